@@ -1,0 +1,124 @@
+/* memvul_b200 -- C ABI of the B200-native MemVul batch-inference hot path.
+ *
+ * The reference (panshengyi/MemVul) is pure Python: its "FFI" for this path is the set of
+ * PyTorch module calls made by
+ *     MemVul/custom_PTM_embedder.py:224-235   PretrainedTransformerEmbedder.forward -> HF BertModel
+ *     MemVul/model_memory.py:90-103           ModelMemory._instance_forward (BertPooler + header)
+ *     MemVul/model_memory.py:105-115          ModelMemory.forward_gold_instances (anchor bank)
+ *     MemVul/model_memory.py:133-147          ModelMemory.forward test branch (match/softmax/argmax)
+ *     MemVul/model_single.py:84-92            ModelSingle.forward (MemVul-m head)
+ * Each entry point below names the call it replaces.  Conventions:
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the library borrows pointers for the duration of the call, allocates nothing on the
+ *     device, and enqueues all work on `stream` (a cudaStream_t passed as void*), asynchronously;
+ *   - return 0 on success, a negative MEMVUL_E_* code on failure; memvul_last_error() gives the
+ *     text of the calling thread's last failure.  No C++ exception crosses the boundary.
+ *   - fp32 = float, fp16 = IEEE binary16 (passed as void*), token ids int64 as AllenNLP emits them.
+ */
+#ifndef MEMVUL_B200_H
+#define MEMVUL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEMVUL_ABI_VERSION 1
+
+enum {
+  MEMVUL_OK = 0,
+  MEMVUL_E_INVALID = -1,   /* bad argument / unsupported shape */
+  MEMVUL_E_CUDA = -2,      /* CUDA runtime / driver error      */
+  MEMVUL_E_WORKSPACE = -3  /* workspace too small              */
+};
+
+/* GEMM epilogues (memvul_gemm_f16) */
+enum {
+  MEMVUL_EPI_BIAS_F16 = 0,       /* out fp16 = A W^T + bias                    */
+  MEMVUL_EPI_BIAS_GELU_F16 = 1,  /* out fp16 = gelu_erf(A W^T + bias)          */
+  MEMVUL_EPI_BIAS_RESID_F32 = 2  /* out fp32 = A W^T + bias + resid (fp32)     */
+};
+
+/* pool/match phases (memvul_pool_match phase_mask); MEMVUL_PM_ALL runs as one cooperative launch */
+enum {
+  MEMVUL_PM_POOL = 1, MEMVUL_PM_HEADER = 2, MEMVUL_PM_UTERM = 4, MEMVUL_PM_MATCH = 8, MEMVUL_PM_FINAL = 16,
+  MEMVUL_PM_ALL = 31
+};
+
+/* One BERT encoder layer; GEMM kernels are fp16 [out,in] row-major (nn.Linear layout), the rest fp32. */
+typedef struct memvul_bert_layer {
+  const void* w_qkv;  const float* b_qkv;   /* [3H,H] rows = query|key|value, [3H] */
+  const void* w_ao;   const float* b_ao;    /* attention.output.dense [H,H], [H]   */
+  const float* ln1_g; const float* ln1_b;   /* attention.output.LayerNorm          */
+  const void* w_ff1;  const float* b_ff1;   /* intermediate.dense [I,H], [I]       */
+  const void* w_ff2;  const float* b_ff2;   /* output.dense [H,I], [H]             */
+  const float* ln2_g; const float* ln2_b;   /* output.LayerNorm                    */
+} memvul_bert_layer;
+
+typedef struct memvul_bert_weights {
+  int32_t hidden, layers, heads, intermediate, vocab, max_pos, type_vocab;
+  float ln_eps;
+  const float* word_emb; const float* pos_emb; const float* type_emb;   /* fp32 tables */
+  const float* emb_ln_g; const float* emb_ln_b;
+  const memvul_bert_layer* layer;           /* HOST array of `layers` entries */
+} memvul_bert_weights;
+
+int memvul_abi_version(void);
+const char* memvul_last_error(void);
+
+/* Bytes of scratch memvul_encoder_forward needs for B sequences padded to S tokens. */
+size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S);
+
+/* Replaces PretrainedTransformerEmbedder.forward / HF BertModel.forward
+ * (custom_PTM_embedder.py:224-235).
+ *   token_ids [B,S] int64; type_ids [B,S] int64 or NULL (all zero, custom_PTM_embedder.py:199-202);
+ *   lens [B] int32 = number of unmasked (prefix) tokens per sequence, 1 <= len <= S;
+ *   hidden_out [B*S, H] fp32 = last_hidden_state (rows of padded tokens are unspecified).
+ * Supported: H in {128, 768} (H % 128 == 0, head_dim == 64), S <= 512, S <= max_pos. */
+int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
+                           const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* bool mask [B,S] (1 byte each, AllenNLP `mask`) -> lens[B]; *bad_flag (device int32) is set to 1 if a
+ * mask is not a non-empty prefix mask.  (custom_PTM_embedder.py:215-216 consumes the mask.) */
+int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* bad_flag, void* stream);
+
+/* Anchor-bank side term: vterm[g,c] = Wv[c] . bank[g]  (the v third of Linear(1536->2),
+ * model_memory.py:141), computed once per bank build (model_memory.py:105-115). */
+int memvul_bank_prepare(const float* bank, const float* w_proj, int G, int D, float* vterm, void* stream);
+
+/* Replaces BertPooler + FeedForward header + match + softmax + argmax + gather
+ * (model_memory.py:99,102,135-147).  cls row b is read at cls + b*cls_stride.
+ * Outputs: u [B,D]; logits, probs [B,G,2]; best_idx [B] int32 (first maximum of probs[:, :, same_idx]);
+ * best_probs [B,2].  Scratch: pooled [B,H], uterm [B,2], best_key [B] (8 bytes each).
+ * phase_mask selects phases (tests); MEMVUL_PM_ALL is the fused single launch.  G may be 0 only when
+ * phase_mask has neither MATCH nor FINAL (bank building uses POOL|HEADER). */
+int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool, const float* b_pool,
+                      const float* w_head, const float* b_head, const float* w_proj, const float* bank,
+                      const float* vterm, int B, int G, int H, int D, int same_idx, float* pooled, float* u,
+                      float* uterm, uint64_t* best_key, float* logits, float* probs, int32_t* best_idx,
+                      float* best_probs, int phase_mask, void* stream);
+
+/* MemVul-m classifier (model_single.py:62-65,88-90): logits = feat Wc^T, probs = softmax. */
+int memvul_single_head(const float* feat, const float* w_cls, int B, int D, float* logits, float* probs,
+                       void* stream);
+
+/* ---- building blocks, exported for the parity tests and the profiler harness ---- */
+/* out = epilogue(A[M,K] fp16 x W[N,K]^T fp16); K % 64 == 0, N % 128 == 0; resid/out leading dim = N. */
+int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
+                    int K, int epilogue, void* stream);
+/* ctx[B*S,H] fp16 = softmax(QK^T/8 + mask)V per head from qkv [B*S,3H] fp16; head_dim 64, S <= 512. */
+int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream);
+/* x32/x16 = LayerNorm(y) rows; x32 or x16 may be NULL; in-place x32 == y allowed. */
+int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16,
+                     int M, int H, void* stream);
+/* K1: LayerNorm(word[ids] + pos + type) -> x32, x16. */
+int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids, int B,
+                           int S, float* x32, void* x16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMVUL_B200_H */

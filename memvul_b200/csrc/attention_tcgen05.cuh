@@ -1,0 +1,256 @@
+// Fused self-attention for one (sequence, head, 128-query tile) per CTA on tcgen05:
+//     ctx = softmax(Q K^T / sqrt(64) + key_mask) V          
+// replacing HF BertSelfAttention's matmul / div / add-mask / softmax / matmul chain
+// (transformers 4.1.0, entered from MemVul/custom_PTM_embedder.py:228) that round-trips a
+// [B,12,S,S] fp32 score tensor through HBM.
+//
+// Input  : qkv fp16 [B*S, 3*H] row-major (Q | K | V column blocks, head h at columns h*64)
+//          read through ONE 2-D TMA map with box {64 cols, 128 rows}, SWIZZLE_128B.
+// Output : ctx fp16 [B*S, H] row-major (head h at columns h*64).
+// Masking: keys >= len[b] are excluded.  The reference adds -10000 to their scores, whose
+//          exp underflows to exactly 0 in fp32, so exclusion is bit-equivalent; fully padded
+//          key blocks and fully padded query tiles are skipped (padded query rows are never
+//          consumed: BertPooler reads row 0 only, MemVul/model_memory.py:99).
+//
+// Warps 0-3 : softmax (one query row per thread; S read from TMEM, P written to smem as the
+//             fp16 A operand of the second MMA, running max / sum in fp32, O rescaled in TMEM)
+// Warp 4    : lane 0 issues the TMA loads and both tcgen05.mma streams.
+// TMEM      : S double buffer 2 x 128 cols, O 64 cols.   Key length <= 512 (4 blocks of 128).
+#pragma once
+#include "ptx.cuh"
+
+namespace mv {
+
+struct AttnCfg {
+  static constexpr int BQ = 128, BKV = 128, DH = 64, MAX_KB = 4;
+  static constexpr int TILE_BYTES = 128 * 64 * 2;          // 16 KB: one {64 x 128} fp16 box
+  static constexpr int P_BYTES = 2 * TILE_BYTES;           // 128 x 128 fp16 = two K-chunks
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 160;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TM_S = 0, TM_O = 256;
+};
+
+__global__ void __launch_bounds__(AttnCfg::THREADS, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int* __restrict__ lens,
+                         __half* __restrict__ ctx, int S, int H) {
+  using C = AttnCfg;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int len = lens[b];
+  const int q0 = qt * C::BQ;
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = static_cast<int>(threadIdx.x & 31);
+  const size_t row_base = static_cast<size_t>(b) * S;
+
+  if (q0 >= len) {
+    // fully padded query tile: deterministic zeros, no tensor work
+    const int rows = min(C::BQ, S - q0);
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+      const int r = i >> 3, u = i & 7;
+      *reinterpret_cast<uint4*>(ctx + (row_base + q0 + r) * H + h * C::DH + u * 8) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [4]
+  uint64_t* v_full = bars + 5;             // [4]
+  uint64_t* s_full = bars + 9;             // [4]  QK^T of block j complete
+  uint64_t* p_full = bars + 13;            // [4]  P_j in smem, S_j drained, O rescaled   (4 warp arrivals)
+  uint64_t* pv_done = bars + 17;           // [4]  P_j V_j accumulated into O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int nkb = (len + C::BKV - 1) / C::BKV;     // 1..4 key blocks; every barrier is used once (parity 0)
+
+  if (warp_idx == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_qkv);
+      mbar_init(q_full, 1);
+      for (int j = 0; j < C::MAX_KB; ++j) {
+        mbar_init(&k_full[j], 1);
+        mbar_init(&v_full[j], 1);
+        mbar_init(&s_full[j], 1);
+        mbar_init(&p_full[j], 4);
+        mbar_init(&pv_done[j], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 4) {
+    if (lane == 0) {
+      // ---------------- TMA: Q, then K/V blocks in consumption order ----------------
+      const int row_q = static_cast<int>(row_base) + q0;
+      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+      tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_q, kEvictFirst);
+      for (int j = 0; j < nkb; ++j) {
+        const int row_k = static_cast<int>(row_base) + j * C::BKV;
+        mbar_arrive_expect_tx(&k_full[j], C::TILE_BYTES);
+        tma_load_2d(smem + C::OFF_K + j * C::TILE_BYTES, &tmap_qkv, &k_full[j], H + h * C::DH, row_k, kEvictLast);
+        mbar_arrive_expect_tx(&v_full[j], C::TILE_BYTES);
+        tma_load_2d(smem + C::OFF_V + j * C::TILE_BYTES, &tmap_qkv, &v_full[j], 2 * H + h * C::DH, row_k,
+                    kEvictLast);
+      }
+      // ---------------- MMA issue ----------------
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);   // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);     // O += P V    (V is N-major)
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + C::OFF_Q));
+      auto issue_qk = [&](int j) {
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + j * C::TILE_BYTES));
+        const uint32_t d = tmem_base + C::TM_S + static_cast<uint32_t>((j & 1) * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
+                      k != 0 ? 1u : 0u);
+        umma_commit(&s_full[j]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < nkb; ++j) {
+        if (j + 1 < nkb) {
+          // S buffer (j+1)&1 was last read for block j-1, whose p_full we already waited on.
+          mbar_wait(&k_full[j + 1], 0);
+          tc_fence_after();
+          issue_qk(j + 1);
+        }
+        mbar_wait(&p_full[j], 0);
+        mbar_wait(&v_full[j], 0);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + C::OFF_P + (j & 1) * C::P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + C::OFF_V + j * C::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // A = P: K-major, two 64-wide K chunks of 16 KB, 32 B per K=16 step inside a chunk.
+          const uint64_t a_desc = umma_desc_sw128(p_addr + (kk >> 2) * C::TILE_BYTES) +
+                                  static_cast<uint64_t>((kk & 3) * 2);
+          // B = V: N-major (64 dh contiguous = one swizzle row per key); 16 keys = 2048 B per step.
+          const uint64_t b_desc = umma_desc_sw128(v_addr + kk * 2048);
+          umma_f16_ss(tmem_base + C::TM_O, a_desc, b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&pv_done[j]);
+      }
+    }
+  } else {
+    // ======================= softmax warps: thread <-> query row =======================
+    const int r = warp_idx * 32 + lane;                       // row in tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp_idx * 32) << 16;
+    const float c = 1.4426950408889634f * 0.125f;             // log2(e) / sqrt(64)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(&s_full[j], 0);
+      tc_fence_after();
+      uint32_t s[4][32];
+      const uint32_t s_addr = tmem_base + lane_addr + C::TM_S + static_cast<uint32_t>((j & 1) * 128);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_addr + cc * 32, s[cc]);
+      tmem_wait_ld();
+      const int valid = min(C::BKV, len - j * C::BKV);         // >= 1
+      float mx = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (cc * 32 + i < valid) ? __uint_as_float(s[cc][i]) : -INFINITY;
+          s[cc][i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      const float m_new = fmaxf(m_run, mx);
+      const float mc = m_new * c;
+      float l_blk = 0.f;
+      uint8_t* p_row = smem + C::OFF_P + (j & 1) * C::P_BYTES + r * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {              // 8 columns -> one 16 B unit of the swizzled row
+          float e[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            e[t] = exp2f(fmaf(__uint_as_float(s[cc][u * 8 + t]), c, -mc));    // exp2(-inf) = 0 for masked keys
+            l_blk += e[t];
+          }
+          uint4 pk;
+          pk.x = pack_half2(e[0], e[1]);
+          pk.y = pack_half2(e[2], e[3]);
+          pk.z = pack_half2(e[4], e[5]);
+          pk.w = pack_half2(e[6], e[7]);
+          const int unit = (cc & 1) * 4 + u;       // 16 B unit inside the 64-column chunk
+          const int chunk = cc >> 1;
+          *reinterpret_cast<uint4*>(p_row + chunk * C::TILE_BYTES + ((unit ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      const float alpha = exp2f((m_run - m_new) * c);          // 0 on the first block (m_run = -inf)
+      if (j > 0) {
+        mbar_wait(&pv_done[j - 1], 0);                         // O holds blocks 0..j-1; P[(j-1)&1] is free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, m_new > m_run)) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t o[32];
+            const uint32_t o_addr = tmem_base + lane_addr + C::TM_O + half * 32;
+            tmem_ld_32x32b_x32(o_addr, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      fence_proxy_async_smem();        // P (generic-proxy stores) -> visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j]);
+    }
+    // ---------------- O / l -> ctx ----------------
+    mbar_wait(&pv_done[nkb - 1], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    __half* orow = ctx + (row_base + q) * H + h * C::DH;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + C::TM_O + half * 32, o);
+      tmem_wait_ld();
+      if (q < S) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 pk;
+          pk.x = pack_half2(__uint_as_float(o[8 * u + 0]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l);
+          pk.y = pack_half2(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
+          pk.z = pack_half2(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
+          pk.w = pack_half2(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + half * 32 + u * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace mv

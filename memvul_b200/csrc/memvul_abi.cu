@@ -1,0 +1,411 @@
+// C-ABI entry points of libmemvul_b200.so (declared in include/memvul_b200.h): argument checks,
+// TMA tensor-map construction (cached), launch configuration.  No torch, no exceptions across the ABI.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/memvul_b200.h"
+#include "attention_tcgen05.cuh"
+#include "gemm_tcgen05.cuh"
+#include "pool_match.cuh"
+#include "rowwise.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(MEMVUL_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------ device info
+struct DeviceInfo {
+  int sms = 0;
+  bool ok = false;
+};
+int device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static std::unordered_map<int, DeviceInfo> cache;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it == cache.end()) {
+    DeviceInfo d;
+    int major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(MEMVUL_E_CUDA, "memvul_b200 needs an sm_100a device (found compute capability %d.x)", major);
+    d.ok = true;
+    it = cache.emplace(dev, d).first;
+  }
+  *out = it->second;
+  return MEMVUL_OK;
+}
+
+// ------------------------------------------------------------------ TMA tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h = h * 1315423911u ^ k.rows;
+    h = h * 1315423911u ^ k.cols;
+    h = h * 1315423911u ^ k.ld;
+    h = h * 1315423911u ^ k.box_rows;
+    return h;
+  }
+};
+// fp16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}, SWIZZLE_128B.
+int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{base, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return MEMVUL_OK;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MEMVUL_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u))
+    return fail(MEMVUL_E_INVALID, "TMA operand must be 16-byte aligned (ptr=%p ld=%llu)", base, (unsigned long long)ld);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MEMVUL_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return MEMVUL_OK;
+}
+
+// ------------------------------------------------------------------ launchers
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
+                const float* resid, void* out, int sms, cudaStream_t st) {
+  using Cfg = mv::GemmCfg<BN>;
+  auto kern = mv::gemm_f16_tcgen05_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, bias, resid, out, N);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+template <int BN>
+int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
+                    const float* resid, void* out, int sms, cudaStream_t st) {
+  switch (epi) {
+    case MEMVUL_EPI_BIAS_F16: return launch_gemm<BN, mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm<BN, mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm<BN, mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st);
+  }
+  return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
+int gemm_impl(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
+              int epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(MEMVUL_E_INVALID, "GEMM with empty shape M=%d N=%d K=%d", M, N, K);
+  if (K % 64 != 0 || N % 128 != 0)
+    return fail(MEMVUL_E_INVALID, "GEMM needs K %% 64 == 0 and N %% 128 == 0 (M=%d N=%d K=%d)", M, N, K);
+  if (!a || !w || !bias || !out) return fail(MEMVUL_E_INVALID, "GEMM null pointer");
+  if (epi == MEMVUL_EPI_BIAS_RESID_F32 && !resid) return fail(MEMVUL_E_INVALID, "GEMM residual epilogue needs resid");
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int tiles_m = (M + 127) / 128;
+  const bool bn256 = (N % 256 == 0) && (tiles_m * (N / 256) >= di.sms);
+  const int BN = bn256 ? 256 : 128;
+  CUtensorMap ta, tb;
+  if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
+  if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, &tb)) return rc;
+  return bn256 ? launch_gemm_epi<256>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st)
+               : launch_gemm_epi<128>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st);
+}
+
+int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || S > 512) return fail(MEMVUL_E_INVALID, "attention needs 1 <= S <= 512 (B=%d S=%d)", B, S);
+  if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  CUtensorMap tq;
+  if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, &tq)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(mv::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  mv::AttnCfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((S + 127) / 128, H / 64, B);
+  mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
+      tq, lens, reinterpret_cast<__half*>(ctx), S, H);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int layernorm_impl(const float* y, const float* g, const float* b, float eps, float* x32, void* x16, int M, int H,
+                   cudaStream_t st) {
+  if (M <= 0) return fail(MEMVUL_E_INVALID, "layernorm with M=%d", M);
+  const int blocks = (M + 7) / 8;
+  if (H == 768)
+    mv::layernorm_rows_kernel<6><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, reinterpret_cast<__half*>(x16), M);
+  else if (H == 128)
+    mv::layernorm_rows_kernel<1><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, reinterpret_cast<__half*>(x16), M);
+  else
+    return fail(MEMVUL_E_INVALID, "layernorm supports H in {128, 768}, got %d", H);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int embed_impl(const memvul_bert_weights* w, const int64_t* ids, const int64_t* tids, int B, int S, float* x32,
+               void* x16, cudaStream_t st) {
+  const int M = B * S;
+  const int blocks = (M + 7) / 8;
+  auto ll = [](const int64_t* p) { return reinterpret_cast<const long long*>(p); };
+  if (w->hidden == 768)
+    mv::embed_layernorm_kernel<6><<<blocks, 256, 0, st>>>(ll(ids), ll(tids), w->word_emb, w->pos_emb, w->type_emb,
+                                                          w->emb_ln_g, w->emb_ln_b, w->ln_eps, x32,
+                                                          reinterpret_cast<__half*>(x16), M, S, w->vocab, w->type_vocab);
+  else if (w->hidden == 128)
+    mv::embed_layernorm_kernel<1><<<blocks, 256, 0, st>>>(ll(ids), ll(tids), w->word_emb, w->pos_emb, w->type_emb,
+                                                          w->emb_ln_g, w->emb_ln_b, w->ln_eps, x32,
+                                                          reinterpret_cast<__half*>(x16), M, S, w->vocab, w->type_vocab);
+  else
+    return fail(MEMVUL_E_INVALID, "embedding supports hidden in {128, 768}, got %d", w->hidden);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+__global__ void mask_to_lens_kernel(const uint8_t* __restrict__ mask, int B, int S, int32_t* lens, int32_t* bad) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int cnt = 0, last = -1;
+  for (int s = lane; s < S; s += 32)
+    if (mask[static_cast<size_t>(b) * S + s]) { ++cnt; last = s; }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if (lane == 0) {
+    lens[b] = cnt;
+    if (cnt == 0 || last != cnt - 1) *bad = 1;     // empty, or not a prefix mask
+  }
+}
+
+struct Workspace {
+  __half* x16; __half* qkv; __half* ctx; __half* ffn;
+  size_t bytes;
+};
+Workspace carve(const memvul_bert_weights* w, int B, int S, void* base) {
+  const size_t M = static_cast<size_t>(B) * S, H = w->hidden, I = w->intermediate;
+  auto up = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  Workspace ws;
+  ws.x16 = reinterpret_cast<__half*>(p + off); off += up(M * H * 2);
+  ws.qkv = reinterpret_cast<__half*>(p + off); off += up(M * 3 * H * 2);
+  ws.ctx = reinterpret_cast<__half*>(p + off); off += up(M * H * 2);
+  ws.ffn = reinterpret_cast<__half*>(p + off); off += up(M * I * 2);
+  ws.bytes = off;
+  return ws;
+}
+
+int check_weights(const memvul_bert_weights* w) {
+  if (!w || !w->layer) return fail(MEMVUL_E_INVALID, "null weights");
+  if (w->hidden != 768 && w->hidden != 128) return fail(MEMVUL_E_INVALID, "hidden must be 768 or 128, got %d", w->hidden);
+  if (w->heads * 64 != w->hidden) return fail(MEMVUL_E_INVALID, "head_dim must be 64 (hidden=%d heads=%d)", w->hidden, w->heads);
+  if (w->intermediate % 128 != 0) return fail(MEMVUL_E_INVALID, "intermediate must be a multiple of 128, got %d", w->intermediate);
+  if (w->layers <= 0) return fail(MEMVUL_E_INVALID, "layers=%d", w->layers);
+  return MEMVUL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int memvul_abi_version(void) { return MEMVUL_ABI_VERSION; }
+const char* memvul_last_error(void) { return g_err; }
+
+size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S) {
+  if (!w || B <= 0 || S <= 0) return 0;
+  return carve(w, B, S, nullptr).bytes;
+}
+
+int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
+                    int K, int epilogue, void* stream) {
+  return gemm_impl(a, w, bias, resid, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream) {
+  if (!qkv || !lens || !ctx) return fail(MEMVUL_E_INVALID, "attention null pointer");
+  return attention_impl(qkv, lens, ctx, B, S, H, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16, int M,
+                     int H, void* stream) {
+  if (!y || !gamma || !beta) return fail(MEMVUL_E_INVALID, "layernorm null pointer");
+  return layernorm_impl(y, gamma, beta, eps, x32, x16, M, H, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids, int B,
+                           int S, float* x32, void* x16, void* stream) {
+  if (!w || !token_ids || !x32 || !x16) return fail(MEMVUL_E_INVALID, "embed null pointer");
+  if (B <= 0 || S <= 0 || S > w->max_pos) return fail(MEMVUL_E_INVALID, "embed needs 1 <= S <= max_pos (B=%d S=%d)", B, S);
+  return embed_impl(w, token_ids, type_ids, B, S, x32, x16, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* bad_flag, void* stream) {
+  if (!mask || !lens || !bad_flag || B <= 0 || S <= 0) return fail(MEMVUL_E_INVALID, "mask_to_lens bad argument");
+  mask_to_lens_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, S, lens, bad_flag);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
+                           const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (int rc = check_weights(w)) return rc;
+  if (!token_ids || !lens || !hidden_out || !workspace) return fail(MEMVUL_E_INVALID, "encoder null pointer");
+  if (B <= 0 || S <= 0 || S > 512 || S > w->max_pos)
+    return fail(MEMVUL_E_INVALID, "encoder needs 1 <= S <= min(512, max_pos) (B=%d S=%d)", B, S);
+  Workspace ws = carve(w, B, S, workspace);
+  if (ws.bytes > workspace_bytes)
+    return fail(MEMVUL_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = B * S, H = w->hidden, I = w->intermediate;
+  float* x32 = hidden_out;
+  if (int rc = embed_impl(w, token_ids, type_ids, B, S, x32, ws.x16, st)) return rc;
+  for (int l = 0; l < w->layers; ++l) {
+    const memvul_bert_layer& L = w->layer[l];
+    if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc;
+    if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st)) return rc;
+    if (int rc = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
+    if (int rc = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
+    if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc;
+    if (int rc = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
+    if (int rc = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
+  }
+  return MEMVUL_OK;
+}
+
+int memvul_bank_prepare(const float* bank, const float* w_proj, int G, int D, float* vterm, void* stream) {
+  if (!bank || !w_proj || !vterm || G <= 0 || D <= 0) return fail(MEMVUL_E_INVALID, "bank_prepare bad argument");
+  mv::bank_vterm_kernel<<<(G + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(bank, w_proj, vterm, G, D);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool, const float* b_pool,
+                      const float* w_head, const float* b_head, const float* w_proj, const float* bank,
+                      const float* vterm, int B, int G, int H, int D, int same_idx, float* pooled, float* u,
+                      float* uterm, uint64_t* best_key, float* logits, float* probs, int32_t* best_idx,
+                      float* best_probs, int phase_mask, void* stream) {
+  if (B <= 0 || H <= 0 || D <= 0 || H % 128 != 0 || H > 768 || D % 4 != 0 || D > 512)
+    return fail(MEMVUL_E_INVALID, "pool_match needs H %% 128 == 0, H <= 768, D %% 4 == 0, D <= 512 (B=%d H=%d D=%d)", B, H, D);
+  if (phase_mask <= 0 || phase_mask > MEMVUL_PM_ALL) return fail(MEMVUL_E_INVALID, "bad phase_mask %d", phase_mask);
+  if ((phase_mask & (MEMVUL_PM_MATCH | MEMVUL_PM_FINAL)) &&
+      (G <= 0 || !bank || !vterm || !logits || !probs || !best_key || !best_idx || !best_probs || !uterm))
+    return fail(MEMVUL_E_INVALID, "pool_match: match phases need a non-empty bank and output buffers (G=%d)", G);
+  if ((phase_mask & MEMVUL_PM_POOL) && (!cls || !w_pool || !b_pool || !pooled)) return fail(MEMVUL_E_INVALID, "pool_match: POOL needs cls/w_pool/b_pool/pooled");
+  if ((phase_mask & MEMVUL_PM_HEADER) && (!w_head || !b_head || !pooled || !u)) return fail(MEMVUL_E_INVALID, "pool_match: HEADER needs w_head/b_head/pooled/u");
+  if ((phase_mask & MEMVUL_PM_UTERM) && (!w_proj || !u || !uterm || !best_key)) return fail(MEMVUL_E_INVALID, "pool_match: UTERM needs w_proj/u/uterm/best_key");
+  if (same_idx != 0 && same_idx != 1) return fail(MEMVUL_E_INVALID, "same_idx must be 0 or 1, got %d", same_idx);
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mv::pool_match_kernel, 256, 0));
+    if (blocks_per_sm < 1) return fail(MEMVUL_E_CUDA, "pool_match kernel does not fit on an SM");
+    if (blocks_per_sm > 4) blocks_per_sm = 4;
+  }
+  const int grid = di.sms * blocks_per_sm;
+  const int nwarps = grid * 8;
+  mv::PoolMatchParams p;
+  p.cls = cls; p.cls_stride = cls_stride;
+  p.wp = w_pool; p.bp = b_pool; p.wh = w_head; p.bh = b_head; p.wproj = w_proj;
+  p.bank = bank; p.vterm = vterm; p.pooled = pooled; p.u = u; p.uterm = uterm;
+  p.best_key = reinterpret_cast<unsigned long long*>(best_key);
+  p.logits = logits; p.probs = probs; p.best_idx = best_idx; p.best_probs = best_probs;
+  p.B = B; p.G = G; p.H = H; p.D = D; p.same_idx = same_idx; p.phase_mask = phase_mask;
+  // b_chunk: aim at ~4 work items per resident warp so the tail is short, but keep each anchor quad's
+  // registers alive across as many queries as possible.
+  const long long units = static_cast<long long>(B) * ((G + 3) / 4);
+  long long bc = units / (4LL * nwarps);
+  if (bc < 1) bc = 1;
+  if (bc > B) bc = B;
+  p.b_chunk = static_cast<int>(bc);
+  if ((phase_mask & MEMVUL_PM_MATCH) && !(phase_mask & (MEMVUL_PM_POOL | MEMVUL_PM_UTERM)))
+    CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(uint64_t) * B, st));
+  const bool multi = (phase_mask & (phase_mask - 1)) != 0;
+  if (multi) {
+    void* args[] = {&p};
+    CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mv::pool_match_kernel), dim3(grid), dim3(256), args, 0, st));
+  } else {
+    mv::pool_match_kernel<<<grid, 256, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return MEMVUL_OK;
+}
+
+int memvul_single_head(const float* feat, const float* w_cls, int B, int D, float* logits, float* probs, void* stream) {
+  if (!feat || !w_cls || !logits || !probs || B <= 0 || D <= 0) return fail(MEMVUL_E_INVALID, "single_head bad argument");
+  mv::single_head_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, w_cls, logits, probs, B, D);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// Fused [CLS] pool + header + CWE-anchor match, all fp32 on CUDA cores,
+// ONE cooperative launch with grid-wide syncs between phases:
+//   P1  pooled = tanh(Wp . h[:,0] + bp)                       AllenNLP BertPooler    (model_memory.py:64,99)
+//   P2  u      = relu(Wh . pooled + bh)                       FeedForward 768->512   (model_memory.py:70,102)
+//   P3  uterm[b,c] = Wu[c] . u[b]                              first third of Linear(1536->2)
+//   P4  logits[b,g,c] = uterm[b,c] + vterm[g,c] + sum_k Wd[c,k] |u[b,k] - v[g,k]|   (model_memory.py:135-141)
+//       p = softmax_c(logits)                                  (:142)
+//       best[b] = argmax_g p[b,g,same]  (first maximum wins)   (:144-145)
+//   P5  best_idx[b], best_probs[b,:] = p[b, best_idx[b], :]     (:146-147)
+// The reference materialises a [B,G,1536] concat tensor; here the separable form is used:
+// the anchor bank v [G,512] is read once per (b-chunk) pass with 128-bit coalesced loads, kept in
+// registers, and only the |u - v| term is O(B*G*512).  vterm = Wv . v is precomputed when the bank is
+// built (bank_vterm_kernel).
+//
+// P4 work item = (4 anchors) x (chunk of BC queries), one warp per item, K split across the 32 lanes.
+#pragma once
+#include <cooperative_groups.h>
+#include "ptx.cuh"
+
+namespace mv {
+namespace cg = cooperative_groups;
+
+struct PoolMatchParams {
+  // inputs
+  const float* cls;        // row b at cls + b * cls_stride  ([CLS] hidden state, H floats)
+  long long cls_stride;
+  const float* wp; const float* bp;      // [H,H], [H]
+  const float* wh; const float* bh;      // [D,H], [D]
+  const float* wproj;                    // [2, 3*D] = [Wu | Wv | Wd]
+  const float* bank;                     // [G,D]
+  const float* vterm;                    // [G,2]
+  // workspace / outputs
+  float* pooled;                         // [B,H]
+  float* u;                              // [B,D]
+  float* uterm;                          // [B,2]
+  unsigned long long* best_key;          // [B]
+  float* logits;                         // [B,G,2]
+  float* probs;                          // [B,G,2]
+  int* best_idx;                         // [B]
+  float* best_probs;                     // [B,2]
+  int B, G, H, D, same_idx, b_chunk, phase_mask;
+};
+
+// out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]); one output column per warp, W row held in registers.
+template <int ACT /*0 tanh, 1 relu*/>
+__device__ __forceinline__ void dense_rows_phase(const float* x, long long x_stride, const float* __restrict__ W,
+                                                 const float* __restrict__ bias, float* out, int B, int N, int K,
+                                                 int gwarp, int nwarps, int lane) {
+  constexpr int MAXV = 6;                       // K <= 768
+  const int nv = K >> 7;                        // float4 per lane (K multiple of 128)
+  for (int n = gwarp; n < N; n += nwarps) {
+    float4 w[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      w[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + i * 128 + lane * 4))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float bn = bias[n];
+    for (int b = 0; b < B; ++b) {
+      const float* xr = x + static_cast<size_t>(b) * x_stride;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (i < nv) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+          acc = fmaf(xv.x, w[i].x, acc);
+          acc = fmaf(xv.y, w[i].y, acc);
+          acc = fmaf(xv.z, w[i].z, acc);
+          acc = fmaf(xv.w, w[i].w, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float v = acc + bn;
+        out[static_cast<size_t>(b) * N + n] = ACT == 0 ? tanhf(v) : fmaxf(v, 0.f);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp, int nwarps, int lane) {
+  constexpr int MAXJ = 4;                       // D <= 512
+  const int D = p.D, G = p.G, B = p.B;
+  const int nd4 = D >> 2;
+  const float* wd0 = p.wproj + 2 * D;
+  const float* wd1 = p.wproj + 3 * D + 2 * D;
+  const int n_gq = (G + 3) >> 2;
+  const int n_bc = (B + p.b_chunk - 1) / p.b_chunk;
+  const int items = n_gq * n_bc;
+  // lane's K slice: float4 index lane + 32*j
+  float4 w0[MAXJ], w1[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int k4 = lane + 32 * j;
+    const bool ok = k4 < nd4;
+    w0[j] = ok ? __ldg(reinterpret_cast<const float4*>(wd0) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w1[j] = ok ? __ldg(reinterpret_cast<const float4*>(wd1) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int item = gwarp; item < items; item += nwarps) {
+    const int gq = item / n_bc, bc = item - gq * n_bc;
+    const int g0 = gq * 4;
+    float4 v[4][MAXJ];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      const int g = min(g0 + gi, G - 1);        // clamp: tail anchors recompute the last row, never stored
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int k4 = lane + 32 * j;
+        v[gi][j] = (k4 < nd4) ? __ldg(reinterpret_cast<const float4*>(p.bank + static_cast<size_t>(g) * D) + k4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const int b_end = min(B, (bc + 1) * p.b_chunk);
+    for (int b = bc * p.b_chunk; b < b_end; ++b) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int k4 = lane + 32 * j;
+        if (k4 < nd4) {
+          const float4 uu = *(reinterpret_cast<const float4*>(p.u + static_cast<size_t>(b) * D) + k4);
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            const float dx = fabsf(uu.x - v[gi][j].x), dy = fabsf(uu.y - v[gi][j].y);
+            const float dz = fabsf(uu.z - v[gi][j].z), dw = fabsf(uu.w - v[gi][j].w);
+            acc[gi * 2 + 0] = fmaf(dx, w0[j].x, acc[gi * 2 + 0]);
+            acc[gi * 2 + 1] = fmaf(dx, w1[j].x, acc[gi * 2 + 1]);
+            acc[gi * 2 + 0] = fmaf(dy, w0[j].y, acc[gi * 2 + 0]);
+            acc[gi * 2 + 1] = fmaf(dy, w1[j].y, acc[gi * 2 + 1]);
+            acc[gi * 2 + 0] = fmaf(dz, w0[j].z, acc[gi * 2 + 0]);
+            acc[gi * 2 + 1] = fmaf(dz, w1[j].z, acc[gi * 2 + 1]);
+            acc[gi * 2 + 0] = fmaf(dw, w0[j].w, acc[gi * 2 + 0]);
+            acc[gi * 2 + 1] = fmaf(dw, w1[j].w, acc[gi * 2 + 1]);
+          }
+        }
+      }
+      // 8 partial sums x 32 lanes -> halving butterfly (9 shuffles): value (lane>>2)&7 ends in every lane
+      float t4[4], t2[2], t1;
+      {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = up ? acc[i] : acc[4 + i];
+          const float keep = up ? acc[4 + i] : acc[i];
+          t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = up ? t4[i] : t4[2 + i];
+          const float keep = up ? t4[2 + i] : t4[i];
+          t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool up = lane & 4;
+        const float send = up ? t2[0] : t2[1];
+        const float keep = up ? t2[1] : t2[0];
+        t1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+      const float other = __shfl_xor_sync(0xffffffffu, t1, 4);     // class-1 partner of a class-0 lane
+      unsigned long long key = 0ull;
+      if ((lane & 7) == 0) {
+        const int gi = lane >> 3;
+        const int g = g0 + gi;
+        if (g < G) {
+          const float l0 = t1 + p.uterm[b * 2 + 0] + __ldg(p.vterm + g * 2 + 0);
+          const float l1 = other + p.uterm[b * 2 + 1] + __ldg(p.vterm + g * 2 + 1);
+          const float m = fmaxf(l0, l1);
+          const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+          const float inv = 1.0f / (e0 + e1);
+          const float p0 = e0 * inv, p1 = e1 * inv;
+          const size_t o = (static_cast<size_t>(b) * G + g) * 2;
+          *reinterpret_cast<float2*>(p.logits + o) = make_float2(l0, l1);
+          *reinterpret_cast<float2*>(p.probs + o) = make_float2(p0, p1);
+          const float ps = p.same_idx == 0 ? p0 : p1;
+          key = (static_cast<unsigned long long>(__float_as_uint(ps)) << 32) |
+                static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(g));
+        }
+      }
+      // max over the 4 anchors of this warp (keys are 0 in the other lanes), one atomic per (b, quad)
+      key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
+      key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
+      if (lane == 0) atomicMax(p.best_key + b, key);
+    }
+  }
+}
+
+enum : int { PM_POOL = 1, PM_HEADER = 2, PM_UTERM = 4, PM_MATCH = 8, PM_FINAL = 16, PM_ALL = 31 };
+
+__global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpb;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  const bool multi = (p.phase_mask & (p.phase_mask - 1)) != 0;     // >1 phase => cooperative launch
+  bool need_sync = false;
+  auto phase_sync = [&]() {
+    if (need_sync && multi) cg::this_grid().sync();
+    need_sync = true;
+  };
+  if (p.phase_mask & PM_POOL) {
+    phase_sync();
+    dense_rows_phase<0>(p.cls, p.cls_stride, p.wp, p.bp, p.pooled, p.B, p.H, p.H, gwarp, nwarps, lane);
+    for (int b = gtid; b < p.B; b += nthreads) p.best_key[b] = 0ull;
+  }
+  if (p.phase_mask & PM_HEADER) {
+    phase_sync();
+    dense_rows_phase<1>(p.pooled, p.H, p.wh, p.bh, p.u, p.B, p.D, p.H, gwarp, nwarps, lane);
+  }
+  if (p.phase_mask & PM_UTERM) {
+    phase_sync();
+    for (int w = gwarp; w < p.B * 2; w += nwarps) {
+      const int b = w >> 1, c = w & 1;
+      const float* wu = p.wproj + c * 3 * p.D;
+      float acc = 0.f;
+      for (int k = lane; k < p.D; k += 32) acc = fmaf(p.u[static_cast<size_t>(b) * p.D + k], __ldg(wu + k), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) p.uterm[w] = acc;
+    }
+    if (!(p.phase_mask & PM_POOL))
+      for (int b = gtid; b < p.B; b += nthreads) p.best_key[b] = 0ull;
+  }
+  if (p.phase_mask & PM_MATCH) {
+    phase_sync();
+    match_phase(p, gwarp, nwarps, lane);
+  }
+  if (p.phase_mask & PM_FINAL) {
+    phase_sync();
+    for (int b = gtid; b < p.B; b += nthreads) {
+      const unsigned long long key = p.best_key[b];
+      const int g = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull));
+      p.best_idx[b] = g;
+      const size_t o = (static_cast<size_t>(b) * p.G + g) * 2;
+      p.best_probs[b * 2 + 0] = p.probs[o];
+      p.best_probs[b * 2 + 1] = p.probs[o + 1];
+    }
+  }
+}
+
+// vterm[g,c] = Wv[c] . bank[g]   (second third of Linear(1536->2); once per bank build)
+__global__ void __launch_bounds__(256) bank_vterm_kernel(const float* __restrict__ bank,
+                                                         const float* __restrict__ wproj, float* __restrict__ vterm,
+                                                         int G, int D) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= G) return;
+  const float* wv0 = wproj + D;
+  const float* wv1 = wproj + 3 * D + D;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float x = bank[static_cast<size_t>(g) * D + k];
+    a0 = fmaf(x, __ldg(wv0 + k), a0);
+    a1 = fmaf(x, __ldg(wv1 + k), a1);
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (lane == 0) {
+    vterm[g * 2 + 0] = a0;
+    vterm[g * 2 + 1] = a1;
+  }
+}
+
+// MemVul-m head (model_single.py:62-65,88-90): logits[b,c] = Wc[c] . h[b]; probs = softmax.  One warp per sample.
+__global__ void __launch_bounds__(256) single_head_kernel(const float* __restrict__ hfeat,
+                                                          const float* __restrict__ wc, float* __restrict__ logits,
+                                                          float* __restrict__ probs, int B, int D) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float x = hfeat[static_cast<size_t>(b) * D + k];
+    a0 = fmaf(x, __ldg(wc + k), a0);
+    a1 = fmaf(x, __ldg(wc + D + k), a1);
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (lane == 0) {
+    const float m = fmaxf(a0, a1);
+    const float e0 = expf(a0 - m), e1 = expf(a1 - m);
+    const float inv = 1.0f / (e0 + e1);
+    logits[b * 2] = a0; logits[b * 2 + 1] = a1;
+    probs[b * 2] = e0 * inv; probs[b * 2 + 1] = e1 * inv;
+  }
+}
+
+}  // namespace mv
