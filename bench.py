@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- MemVul batch-inference hot path on B200 (BASELINE.json metric: issue-reports/sec).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...          # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1], "C2"): predict_memory full CWE memory, bert-base, seq_len 512,
+batch 64 per GPU, 129 anchors, synthetic ids / seeded random weights (no checkpoint or dataset exists
+offline).  A step = one batch through the test branch of ``ModelMemory.forward``: encoder (12 layers) +
+fused pool/header/match/softmax/argmax.  N > 1: one process per GPU (torchrun), weak scaling (64 issue
+reports per GPU), weights and bank replicated, one NCCL all-gather of the shard results per step.
+
+One JSON line on rank 0:
+  value      issues/s over all GPUs, device-timed (CUDA events, max over ranks), inputs resident in HBM
+  e2e        same metric through ``ModelMemory.forward`` with HOST (pinned) inputs: H2D of ids/mask/type
+             ids/labels and D2H of probs [B,G,2] + best probs/idx inside the timed region
+  roofline   the tcgen05 GEMM kernel (dominant: ~70 % of the step): algorithmic FLOPs / live CUDA-event time
+             vs MEASURED_PEAKS.json's sustained bf16 figure
+  kernels    live per-kernel-class device time of one profiled step (CUDA events around every launch)
+  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) timed on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, SEQ, ANCHORS, SEED = 64, 512, 129, 2021
+METRIC, UNIT = "issue-reports/sec, bert-base seq512 + CWE memory", "issues/s"
+
+
+def flops_per_issue(s: int) -> float:
+    """SURVEY.md 8d / BASELINE.md 4: algorithmic FLOPs of the reference per issue report of length s."""
+    return 12.0 * (14155776.0 * s + 3072.0 * s * s) + 2 * 768 ** 2 + 2 * 768 * 512
+
+
+def gemm_flops_per_step(batch: int, s: int) -> float:
+    """FLOPs executed by the four tcgen05 GEMMs of all 12 layers for one batch (2*M*N*K each)."""
+    m = batch * s
+    return 12.0 * 2.0 * m * (768 * 2304 + 768 * 768 + 768 * 3072 + 3072 * 768)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"src": "measured", "tflops_sustained": d.get("bf16_tflops_sustained"), "tflops": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs")}
+    return {"src": "fallback", "tflops_sustained": 1400.0, "tflops": 1590.0, "hbm_gbs": 6650.0}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_throughput(budget_s: float = 12.0, batch: int = 8):
+    """The reference's CPU path (oracle port) on this box's host cores: bounded sample of the same workload."""
+    import torch
+    from oracle import memvul_oracle as O          # the ONE place the product benchmark touches the oracle: the baseline leg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synthetic_state_dict(O.BERT_BASE, SEED)
+    ids, mask, tids = O.synthetic_ids(batch, SEQ, seed=SEED)
+    g = torch.Generator().manual_seed(SEED)
+    bank = torch.relu(torch.randn(ANCHORS, 512, generator=g) * 0.3)
+    with torch.no_grad():
+        O.memory_forward(sd, ids[:2], mask[:2], tids[:2], bank, 0)            # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            O.memory_forward(sd, ids, mask, tids, bank, 0)
+            n += batch
+            dt = time.perf_counter() - t0
+            if dt > budget_s or n >= 64 * 4:
+                break
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} issue reports (batches of {batch}, S={SEQ}, G={ANCHORS}) in {dt:.1f}s, torch {torch.__version__} "
+                      f"fp32 CPU, {torch.get_num_threads()} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    import torch
+    from oracle import memvul_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synthetic_state_dict(O.BERT_BASE, SEED)
+    b = 8                                             # bounded sample of the C2 batch per step
+    ids, mask, tids = O.synthetic_ids(b, SEQ, seed=SEED)
+    g = torch.Generator().manual_seed(SEED)
+    bank = torch.relu(torch.randn(ANCHORS, 512, generator=g) * 0.3)
+    with torch.no_grad():
+        for _ in range(min(warm, 2)):
+            O.memory_forward(sd, ids, mask, tids, bank, 0)
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            O.memory_forward(sd, ids, mask, tids, bank, 0)
+            done += 1
+            if time.perf_counter() - t0 > 150:
+                break
+        dt = time.perf_counter() - t0
+    v = done * b / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": min(warm, 2), "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2 predict_memory bert-base S={SEQ} G={ANCHORS}; CPU sample of {b} issue reports per step",
+                       "note": "reference = CPU fp32 PyTorch restatement of ModelMemory.forward (oracle port); AllenNLP is not installable offline"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{done} steps x {b} issue reports, S={SEQ}, {torch.get_num_threads()} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from memvul_b200 import native
+    from memvul_b200.dist import gather_match
+    from memvul_b200.synthetic import BERT_BASE, build_memory_model, synthetic_ids
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (memvul_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warm = args.steps, max(args.warmup, 3)
+
+    model, _ = build_memory_model(BERT_BASE, SEED, device=dev)
+    # anchor bank: 129 synthetic anchors (len 64..512) encoded by the model itself, in the reference's 128 + rest chunks
+    g = torch.Generator().manual_seed(SEED + 1)
+    a_lens = torch.randint(64, SEQ + 1, (ANCHORS,), generator=g).tolist()
+    with torch.no_grad():
+        for c0, c1 in ((0, 128), (128, ANCHORS)):
+            lens_c = a_lens[c0:c1]
+            ids, mask, tids = synthetic_ids(len(lens_c), max(lens_c), lens=lens_c, seed=SEED + 2 + c0)
+            model.forward_gold_instances({"tokens": {"token_ids": ids.to(dev), "mask": mask.to(dev), "type_ids": tids.to(dev)}},
+                                         [{"type": "golden", "instance": [{"label": f"CWE-{c0 + i}"}]} for i in range(len(lens_c))])
+    B = B_PER_GPU
+    ids_h, mask_h, tids_h = (t.pin_memory() for t in synthetic_ids(B, SEQ, seed=SEED + 100 + rank))
+    label_h = (torch.arange(B) % 301 == 0).long().pin_memory()          # ~1:300 CIR:NCIR, labels do not change compute
+    meta = [{"type": "unlabel", "instance": [{"label": "neg", "Issue_Url": f"synthetic/{rank}/{i}"}]} for i in range(B)]
+    ids_d, mask_d, tids_d = ids_h.to(dev), mask_h.to(dev), tids_h.to(dev)
+    sample_d = {"tokens": {"token_ids": ids_d, "mask": mask_d, "type_ids": tids_d}}
+    counts = [B] * world
+
+    def step_resident():
+        res = model.match_batch(sample_d)
+        if world > 1:
+            res = gather_match(res, counts, full=True)
+        return res
+
+    def step_e2e():
+        s = {"tokens": {"token_ids": ids_h.to(dev, non_blocking=True), "mask": mask_h.to(dev, non_blocking=True),
+                        "type_ids": tids_h.to(dev, non_blocking=True)}}
+        out = model(sample1=s, label=label_h.to(dev, non_blocking=True), metadata=meta)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, after=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for _ in range(n):
+            last = fn()
+        if after is not None:
+            after(last)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for _ in range(warm):
+            step_resident()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = native.launch_count()
+        ms_res = timed(step_resident, steps)
+        launches = native.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+
+        for _ in range(2):
+            step_e2e()["probs"].numpy()
+
+        def drain(last):                      # the step's result is read on the host inside the timed region
+            last["probs"].numpy()
+            model.get_metrics(reset=False)
+        ms_e2e = timed(step_e2e, steps, after=drain)
+        model.get_metrics(reset=True)
+
+        # live per-kernel timing: same step with CUDA events around every launch
+        native.profile_enable(True)
+        native.profile_read()
+        prof_steps = 2
+        for _ in range(prof_steps):
+            model.match_batch(sample_d)
+        prof = native.profile_read()
+        native.profile_enable(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = B * world
+    value = total * steps / (ms_res / 1e3)
+    e2e_v = total * steps / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+    gemm_ms = sum(prof[k]["ms"] for k in prof if k.startswith("gemm_")) / prof_steps
+    gemm_launches = sum(prof[k]["launches"] for k in prof if k.startswith("gemm_")) // prof_steps
+    gflops = gemm_flops_per_step(B, SEQ)
+    achieved = gflops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    step_ms_prof = sum(v["ms"] for v in prof.values()) / prof_steps
+    kernels = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "launches_per_step": v["launches"] // prof_steps,
+                   "share": round(v["ms"] / prof_steps / step_ms_prof, 4) if step_ms_prof else None}
+               for k, v in prof.items() if v["launches"]}
+    h2d = ids_h.numel() * 8 + tids_h.numel() * 8 + mask_h.numel() + label_h.numel() * 8
+    d2h = B * ANCHORS * 2 * 4 + B * 2 * 4 + B * 4 + 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate/residual (reference: f32)", "data": "synthetic",
+        "config": {"workload": f"C2 predict_memory: bert-base S={SEQ}, {B} issue reports/GPU, {ANCHORS}-anchor CWE memory",
+                   "global_batch": total, "seq_len": SEQ, "anchors": ANCHORS, "parallelism": f"batch-shard x{world}",
+                   "l2": "per-step working set ~650 MB > 126 MB L2 (no flush needed)", "weights": f"seeded random, seed {SEED}"},
+        "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "ModelMemory.forward(sample1, label, metadata) with pinned host inputs; probs read on host"},
+        "gpu_launches": int(launches),
+        "tensor_utilisation": {"algorithmic_tflops": flops_per_issue(SEQ) * value / 1e12,
+                               "frac_of_peak": flops_per_issue(SEQ) * value / 1e12 / world / peaks["tflops_sustained"],
+                               "peak": peaks["tflops_sustained"], "peak_src": peaks["src"] + " bf16 sustained"},
+        "roofline": {"kernel": "gemm_f16_tcgen05_kernel (QKV, attn-out, FFN up/down; all 12 layers)", "bound": "tensor",
+                     "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops_sustained"] if achieved else None, "traffic": None,
+                     "peak_src": peaks["src"] + " (bf16 cuBLAS, sustained: kernel timed inside a long step)",
+                     "flops_per_launch": gflops / gemm_launches if gemm_launches else None,
+                     "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None, "launches_per_step": gemm_launches},
+        "kernels": kernels,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_oracle_throughput()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and args.impl == "native":
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

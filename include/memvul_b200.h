@@ -118,6 +118,19 @@ int memvul_layernorm(const float* y, const float* gamma, const float* beta, floa
 int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids, int B,
                            int S, float* x32, void* x16, void* stream);
 
+/* ---- measurement hooks (bench.py) ----
+ * Kernel classes, in the order memvul_profile_read fills them:
+ *   0 embed_ln, 1 gemm_qkv, 2 attention, 3 gemm_attn_out, 4 layernorm, 5 gemm_ffn_up, 6 gemm_ffn_down,
+ *   7 pool_match, 8 other. */
+#define MEMVUL_KERNEL_CLASSES 9
+/* Number of kernels this library has launched in the calling process (all threads). */
+long long memvul_launch_count(void);
+/* When enabled, every launch is bracketed by CUDA events on its stream (adds ~2 us per launch). */
+int memvul_profile_enable(int on);
+/* cudaDeviceSynchronize(), then per-class summed device milliseconds and launch counts since the last
+ * read; returns MEMVUL_KERNEL_CLASSES (or a negative error). */
+int memvul_profile_read(int n_classes, double* ms_out, long long* count_out);
+
 #ifdef __cplusplus
 }
 #endif

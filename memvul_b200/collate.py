@@ -1,0 +1,50 @@
+"""Batch collation for ``reader_memory`` instances: what AllenNLP's ``allennlp_collate`` +
+``TextField.as_tensor`` + ``move_to_device`` do for this path (SURVEY.md 8b "Tensor input layout").
+
+An instance is a dict ``{"sample1": {"token_ids": [...], "type_ids": [...]}, "label": int|None,
+"metadata": {...}}``.  A batch is padded to its own longest sequence:
+``sample1 = {"tokens": {"token_ids": i64[B,S], "mask": bool[B,S], "type_ids": i64[B,S]}}``, ``label`` i64[B],
+``metadata`` list.  Host tensors are built in pinned memory and copied asynchronously.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import torch
+
+
+def collate_instances(instances: List[Dict[str, Any]], device: Optional[torch.device] = None,
+                      pad_to: Optional[int] = None) -> Dict[str, Any]:
+    B = len(instances)
+    if B == 0:
+        raise ValueError("cannot collate an empty batch")
+    lens = [len(i["sample1"]["token_ids"]) for i in instances]
+    if min(lens) == 0:
+        raise ValueError("instance with zero tokens")
+    S = max(lens) if pad_to is None else max(pad_to, max(lens))
+    pin = device is not None and torch.device(device).type == "cuda" and torch.cuda.is_available()
+    ids = torch.zeros(B, S, dtype=torch.int64, pin_memory=pin)
+    tids = torch.zeros(B, S, dtype=torch.int64, pin_memory=pin)
+    mask = torch.zeros(B, S, dtype=torch.bool, pin_memory=pin)
+    for b, inst in enumerate(instances):
+        t = inst["sample1"]
+        n = lens[b]
+        ids[b, :n] = torch.as_tensor(t["token_ids"], dtype=torch.int64)
+        if t.get("type_ids") is not None:
+            tids[b, :n] = torch.as_tensor(t["type_ids"], dtype=torch.int64)
+        mask[b, :n] = True
+    batch: Dict[str, Any] = {}
+    if device is not None:
+        ids, tids, mask = (x.to(device, non_blocking=True) for x in (ids, tids, mask))
+    batch["sample1"] = {"tokens": {"token_ids": ids, "mask": mask, "type_ids": tids}}
+    if all(i.get("label") is not None for i in instances):
+        lab = torch.tensor([int(i["label"]) for i in instances], dtype=torch.int64)
+        batch["label"] = lab.to(device, non_blocking=True) if device is not None else lab
+    batch["metadata"] = [i["metadata"] for i in instances]
+    return batch
+
+
+def batches(instances: List[Dict[str, Any]], batch_size: int):
+    """``shuffle: false`` sequential batching (config_memory.json:50-57)."""
+    for i in range(0, len(instances), batch_size):
+        yield instances[i:i + batch_size]

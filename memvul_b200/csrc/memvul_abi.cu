@@ -6,8 +6,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/memvul_b200.h"
 #include "attention_tcgen05.cuh"
@@ -32,6 +34,50 @@ int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess)                                                                  \
       return fail(MEMVUL_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
+
+
+// ------------------------------------------------------------------ launch accounting / per-kernel timing
+// Always-on launch counter (bench.py's "gpu_launches") and an opt-in mode that brackets every launch with
+// CUDA events on the launching stream so bench.py can report per-kernel durations from the live run.
+enum KernelClass : int {
+  KC_EMBED_LN = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_ATTN_OUT, KC_LAYERNORM, KC_GEMM_FFN_UP, KC_GEMM_FFN_DOWN,
+  KC_POOL_MATCH, KC_OTHER, KC_COUNT
+};
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+thread_local int g_cls = KC_OTHER;
+
+cudaEvent_t prof_event() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct LaunchScope {
+  cudaStream_t st; cudaEvent_t e0 = nullptr; int cls;
+  LaunchScope(int c, cudaStream_t s) : st(s), cls(c) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on.load(std::memory_order_relaxed)) { e0 = prof_event(); cudaEventRecord(e0, st); }
+  }
+  ~LaunchScope() {
+    if (e0) {
+      cudaEvent_t e1 = prof_event();
+      cudaEventRecord(e1, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof_recs.push_back({cls, e0, e1});
+    }
+  }
+};
+struct ClassScope {
+  int prev;
+  explicit ClassScope(int c) : prev(g_cls) { g_cls = c; }
+  ~ClassScope() { g_cls = prev; }
+};
 
 // ------------------------------------------------------------------ device info
 struct DeviceInfo {
@@ -140,6 +186,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
   }
   const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
+  LaunchScope ls(g_cls, st);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, bias, resid, out, N);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
@@ -189,6 +236,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
     attr_set = true;
   }
   dim3 grid((S + 127) / 128, H / 64, B);
+  LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
       tq, lens, reinterpret_cast<__half*>(ctx), S, H);
   CUDA_TRY(cudaGetLastError());
@@ -199,6 +247,7 @@ int layernorm_impl(const float* y, const float* g, const float* b, float eps, fl
                    cudaStream_t st) {
   if (M <= 0) return fail(MEMVUL_E_INVALID, "layernorm with M=%d", M);
   const int blocks = (M + 7) / 8;
+  LaunchScope ls(KC_LAYERNORM, st);
   if (H == 768)
     mv::layernorm_rows_kernel<6><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, reinterpret_cast<__half*>(x16), M);
   else if (H == 128)
@@ -214,6 +263,7 @@ int embed_impl(const memvul_bert_weights* w, const int64_t* ids, const int64_t* 
   const int M = B * S;
   const int blocks = (M + 7) / 8;
   auto ll = [](const int64_t* p) { return reinterpret_cast<const long long*>(p); };
+  LaunchScope ls(KC_EMBED_LN, st);
   if (w->hidden == 768)
     mv::embed_layernorm_kernel<6><<<blocks, 256, 0, st>>>(ll(ids), ll(tids), w->word_emb, w->pos_emb, w->type_emb,
                                                           w->emb_ln_g, w->emb_ln_b, w->ln_eps, x32,
@@ -309,6 +359,7 @@ int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_id
 
 int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* bad_flag, void* stream) {
   if (!mask || !lens || !bad_flag || B <= 0 || S <= 0) return fail(MEMVUL_E_INVALID, "mask_to_lens bad argument");
+  LaunchScope ls(KC_OTHER, static_cast<cudaStream_t>(stream));
   mask_to_lens_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, S, lens, bad_flag);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
@@ -330,19 +381,47 @@ int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_id
   if (int rc = embed_impl(w, token_ids, type_ids, B, S, x32, ws.x16, st)) return rc;
   for (int l = 0; l < w->layers; ++l) {
     const memvul_bert_layer& L = w->layer[l];
-    if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc;
+    { ClassScope cs(KC_GEMM_QKV);
+    if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
     if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st)) return rc;
-    if (int rc = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
+    { ClassScope cs(KC_GEMM_ATTN_OUT);
+    if (int rc = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
     if (int rc = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
-    if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc;
-    if (int rc = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
+    { ClassScope cs(KC_GEMM_FFN_UP);
+    if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc; }
+    { ClassScope cs(KC_GEMM_FFN_DOWN);
+    if (int rc = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
     if (int rc = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
   }
   return MEMVUL_OK;
 }
 
+
+long long memvul_launch_count(void) { return g_launches.load(); }
+
+int memvul_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return MEMVUL_OK;
+}
+
+int memvul_profile_read(int n_classes, double* ms_out, long long* count_out) {
+  if (n_classes < KC_COUNT || !ms_out || !count_out) return fail(MEMVUL_E_INVALID, "profile_read needs %d slots", (int)KC_COUNT);
+  CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n_classes; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (const ProfRec& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { ms_out[r.cls] += ms; count_out[r.cls] += 1; }
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  return KC_COUNT;
+}
+
 int memvul_bank_prepare(const float* bank, const float* w_proj, int G, int D, float* vterm, void* stream) {
   if (!bank || !w_proj || !vterm || G <= 0 || D <= 0) return fail(MEMVUL_E_INVALID, "bank_prepare bad argument");
+  LaunchScope ls(KC_OTHER, static_cast<cudaStream_t>(stream));
   mv::bank_vterm_kernel<<<(G + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(bank, w_proj, vterm, G, D);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
@@ -391,6 +470,7 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   if ((phase_mask & MEMVUL_PM_MATCH) && !(phase_mask & (MEMVUL_PM_POOL | MEMVUL_PM_UTERM)))
     CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(uint64_t) * B, st));
   const bool multi = (phase_mask & (phase_mask - 1)) != 0;
+  LaunchScope ls(KC_POOL_MATCH, st);
   if (multi) {
     void* args[] = {&p};
     CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mv::pool_match_kernel), dim3(grid), dim3(256), args, 0, st));
@@ -403,6 +483,7 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
 
 int memvul_single_head(const float* feat, const float* w_cls, int B, int D, float* logits, float* probs, void* stream) {
   if (!feat || !w_cls || !logits || !probs || B <= 0 || D <= 0) return fail(MEMVUL_E_INVALID, "single_head bad argument");
+  LaunchScope ls(KC_OTHER, static_cast<cudaStream_t>(stream));
   mv::single_head_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, w_cls, logits, probs, B, D);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;

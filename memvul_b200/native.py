@@ -68,7 +68,10 @@ class BertWeightsC(ctypes.Structure):
 
 EXPORTS = ["memvul_abi_version", "memvul_last_error", "memvul_encoder_workspace_bytes", "memvul_encoder_forward",
            "memvul_mask_to_lens", "memvul_bank_prepare", "memvul_pool_match", "memvul_single_head",
-           "memvul_gemm_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm"]
+           "memvul_gemm_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm",
+           "memvul_launch_count", "memvul_profile_enable", "memvul_profile_read"]
+KERNEL_CLASSES = ["embed_ln", "gemm_qkv", "attention", "gemm_attn_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down",
+                  "pool_match", "other"]
 
 
 def lib() -> ctypes.CDLL:
@@ -95,8 +98,11 @@ def lib() -> ctypes.CDLL:
             L.memvul_attention_f16.argtypes = [vp, vp, vp, i32, i32, i32, vp]
             L.memvul_layernorm.argtypes = [vp, vp, vp, f32, vp, vp, i32, i32, vp]
             L.memvul_embed_layernorm.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, i32, i32, vp, vp, vp]
+            L.memvul_launch_count.restype = ctypes.c_longlong
+            L.memvul_profile_enable.argtypes = [i32]
+            L.memvul_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
             for name in EXPORTS:
-                if name not in ("memvul_last_error", "memvul_encoder_workspace_bytes"):
+                if name not in ("memvul_last_error", "memvul_encoder_workspace_bytes", "memvul_launch_count"):
                     getattr(L, name).restype = ctypes.c_int
             if L.memvul_abi_version() != 1:
                 raise NativeError("libmemvul_b200.so ABI version mismatch")
@@ -225,7 +231,7 @@ def pool_match(cls: torch.Tensor, cls_stride: int, B: int, w_pool, b_pool, w_hea
     """Fused pool + header + match.  Returns dict(u, pooled[, logits, probs, best_idx, best_probs])."""
     dev = w_pool.device
     H = w_pool.shape[0]
-    D = w_head.shape[0]
+    D = w_head.shape[0] if w_head is not None else 4
     G = 0 if bank is None else bank.shape[0]
     f = dict(dtype=torch.float32, device=dev)
     pooled = torch.empty(B, H, **f) if pooled is None else pooled
@@ -302,3 +308,23 @@ def embed_layernorm(w: PackedBert, token_ids: torch.Tensor, type_ids: Optional[t
     _check(lib().memvul_embed_layernorm(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), B, S,
                                         x32.data_ptr(), x16.data_ptr(), _stream()))
     return x32, x16
+
+
+# ---- measurement hooks ----
+def launch_count() -> int:
+    return int(lib().memvul_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    _check(lib().memvul_profile_enable(1 if on else 0))
+
+
+def profile_read() -> Dict[str, Dict[str, float]]:
+    """Synchronises the device; {kernel class: {"ms": summed device ms, "launches": n}} since the last read."""
+    n = len(KERNEL_CLASSES)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_longlong * n)()
+    rc = lib().memvul_profile_read(n, ms, cnt)
+    if rc < 0:
+        _check(rc)
+    return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(KERNEL_CLASSES)}

@@ -1,0 +1,171 @@
+"""Batch-inference driver: the B200 counterpart of the reference's ``predict_memory.py``.
+
+  * ``load_archive``  -- ``allennlp.models.archival.load_archive`` for a ``model.tar.gz`` (config.json +
+                         vocabulary/ + weights.th) with dict overrides (predict_memory.py:60-67).
+  * ``test_siamese``  -- predict_memory.py:49-114: build the anchor bank in chunks of 128 (:81-83), then
+                         stream the evaluation data through ``ModelMemory.forward`` batch by batch, writing
+                         one JSON array per batch per line (what AllenNLP ``evaluate`` does with
+                         ``predictions_output_file``), and return ``model.get_metrics(reset=True)``.
+  * ``cal_metrics`` / ``model_measure`` -- predict_memory.py:117-197: max over anchors -> threshold -> pos/neg,
+                         confusion matrix, ROC-AUC, average precision.
+Host work is overlapped with the GPU: batch i+1 is collated and enqueued before batch i's results are
+turned into JSON.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import logging
+import os
+import tarfile
+import tempfile
+from typing import Any, Dict, Iterable, List, Optional
+
+import numpy as np
+import torch
+
+from .collate import batches, collate_instances
+from .custom_metric import average_precision, roc_auc
+from .registrable import DatasetReader, Model, Vocabulary
+
+logger = logging.getLogger(__name__)
+
+
+def _merge(base: Dict[str, Any], over: Dict[str, Any]) -> Dict[str, Any]:
+    out = copy.deepcopy(base)
+    for k, v in (over or {}).items():
+        out[k] = _merge(out[k], v) if isinstance(v, dict) and isinstance(out.get(k), dict) else copy.deepcopy(v)
+    return out
+
+
+class Archive:
+    def __init__(self, model, config, dataset_reader, validation_dataset_reader):
+        self.model, self.config = model, config
+        self.dataset_reader, self.validation_dataset_reader = dataset_reader, validation_dataset_reader
+
+
+def load_archive(archive_file: str, weights_file: Optional[str] = None, cuda_device: int = -1,
+                 overrides: Optional[Dict[str, Any]] = None) -> Archive:
+    """``archive_file``: a ``model.tar.gz`` or an already-extracted serialization directory."""
+    tmp = None
+    if os.path.isdir(archive_file):
+        root = archive_file
+    else:
+        tmp = tempfile.TemporaryDirectory()
+        with tarfile.open(archive_file, "r:*") as tar:
+            tar.extractall(tmp.name, filter="data")
+        root = tmp.name
+    with open(os.path.join(root, "config.json"), encoding="utf-8") as f:
+        config = _merge(json.load(f), overrides or {})
+    vocab = Vocabulary.from_files(os.path.join(root, "vocabulary"))
+    model_cfg = dict(config["model"])
+    model = Model.from_params(model_cfg, vocab=vocab)
+    state = torch.load(weights_file or os.path.join(root, "weights.th"), map_location="cpu")
+    state = {k: v for k, v in state.items() if not k.endswith("position_ids")}      # authorized_missing_keys
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f"archive weights do not match the model: missing={missing[:5]} unexpected={unexpected[:5]}")
+    if cuda_device >= 0:
+        model.cuda(cuda_device)
+    reader = DatasetReader.from_params(dict(config["dataset_reader"])) if "dataset_reader" in config else None
+    vreader = DatasetReader.from_params(dict(config["validation_dataset_reader"])) \
+        if "validation_dataset_reader" in config else reader
+    if tmp is not None:
+        tmp.cleanup()
+    return Archive(model, config, reader, vreader)
+
+
+def build_memory(model, golden_instances: List[Dict[str, Any]], chunk: int = 128) -> None:
+    """predict_memory.py:81-83: first 128 anchors, then the rest, through ``forward_on_instances``."""
+    model.forward_on_instances(golden_instances[:chunk])
+    if len(golden_instances) > chunk:
+        model.forward_on_instances(golden_instances[chunk:])
+
+
+def evaluate(model, instances: Iterable[Dict[str, Any]], batch_size: int, device: torch.device,
+             predictions_output_file: Optional[str] = None, output_file: Optional[str] = None) -> Dict[str, Any]:
+    """AllenNLP ``evaluate`` for this model: forward every batch under no_grad, write readable predictions."""
+    instances = list(instances)
+    pred_f = open(predictions_output_file, "w", encoding="utf-8") if predictions_output_file else None
+    prev = None
+    with torch.no_grad():
+        for chunk in batches(instances, batch_size):
+            batch = collate_instances(chunk, device)
+            out = model(**batch)
+            if prev is not None and pred_f is not None:       # batch i-1's host work overlaps batch i's kernels
+                pred_f.write(json.dumps(model.make_output_human_readable(prev)) + "\n")
+            prev = out
+        if prev is not None and pred_f is not None:
+            pred_f.write(json.dumps(model.make_output_human_readable(prev)) + "\n")
+    if pred_f:
+        pred_f.close()
+    metrics = model.get_metrics(reset=True)
+    if output_file:
+        with open(output_file, "w", encoding="utf-8") as f:
+            json.dump(metrics, f, indent=4, default=float)
+    return metrics
+
+
+def test_siamese(archive_file, input_file, input_golden_file, test_config=None, weights_file=None, output_file=None,
+                 predictions_output_file=None, batch_size=64, cuda_device=0, seed=2021, package="MemVul",
+                 batch_weight_key="", file_friendly_logging=False) -> Dict[str, Any]:
+    archive = load_archive(archive_file, weights_file=weights_file, cuda_device=cuda_device, overrides=test_config or {})
+    model = archive.model
+    model.eval()
+    for r in (archive.dataset_reader, archive.validation_dataset_reader):
+        if r is not None and hasattr(r, "index_with"):
+            r.index_with(model.vocab)
+    logger.info("Reading golden data from %s", input_golden_file)
+    golden = list(archive.validation_dataset_reader.read(input_golden_file))
+    build_memory(model, golden)
+    logger.info("Reading evaluation data from %s", input_file)
+    loader_cfg = archive.config.get("validation_data_loader") or archive.config.get("data_loader") or {}
+    bs = batch_size or loader_cfg.get("batch_size", 64)
+    device = torch.device(f"cuda:{cuda_device}")
+    metrics = evaluate(model, archive.dataset_reader.read(input_file), bs, device,
+                       predictions_output_file=predictions_output_file, output_file=output_file)
+    logger.info("Finished evaluating.")
+    return metrics
+
+
+def model_measure(test_label, pred, pred_score, sample_id=None):
+    y = np.asarray(test_label).astype(bool)
+    p = np.asarray(pred).astype(bool)
+    TP, FN = int(np.sum(p & y)), int(np.sum(~p & y))
+    TN, FP = int(np.sum(~p & ~y)), int(np.sum(p & ~y))
+    pd = TP / (TP + FN) if TP + FN else 0
+    prec = TP / (TP + FP) if TP + FP else 0
+    f1 = 2 * pd * prec / (pd + prec) if pd + prec else 0
+    from sklearn import metrics as skm
+    fpr, tpr, _ = skm.roc_curve(test_label, pred_score, pos_label=1)
+    result = {"TP": TP, "FN": FN, "TN": TN, "FP": FP, "pd&recall": pd, "prec": prec, "f1": f1,
+              "ap": average_precision(test_label, pred_score), "auc": roc_auc(test_label, pred_score)}
+    return result, fpr, tpr
+
+
+def vote(rows: List[Dict[str, Any]], thres: float = 0.5) -> List[Dict[str, Any]]:
+    """predict_memory.py:168-177: ``prob`` = max over anchors of P(same); ``predict`` = pos iff prob >= thres."""
+    for s in rows:
+        vote_prob = np.max(list(s["predict"].values()))
+        s["prob"] = vote_prob
+        s["predict"] = "pos" if vote_prob >= thres else "neg"
+    return rows
+
+
+def cal_metrics(result_file: str, thres: float = 0.5, out_file: Optional[str] = None) -> Dict[str, Any]:
+    rows: List[Dict[str, Any]] = []
+    with open(result_file, encoding="utf-8") as f:
+        for line in f:
+            if line.strip():
+                rows.extend(json.loads(line))
+    vote(rows, thres)
+    conv = {"pos": 1, "neg": 0}
+    pred = [conv[r["predict"]] for r in rows]
+    label = [0 if r["label"] == "neg" else 1 for r in rows]
+    score = [r["prob"] for r in rows]
+    metrics, _, _ = model_measure(label, pred, score, [r["Issue_Url"] for r in rows])
+    metrics["thres"] = thres
+    if out_file:
+        with open(out_file, "w", encoding="utf-8") as f:
+            json.dump(metrics, f, indent=4, default=float)
+    return metrics

@@ -1,0 +1,74 @@
+"""The C-ABI shared library builds for sm_100a, loads without a GPU and exports every symbol that
+include/memvul_b200.h declares; argument validation answers before any CUDA work."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported(native_lib):
+    hdr = open(os.path.join(ROOT, "include", "memvul_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(memvul_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(native_lib, name), f"{name} declared in the header but not exported"
+    from memvul_b200 import native
+    assert sorted(native.EXPORTS) == declared
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma():
+    from memvul_b200 import native
+    native.build()
+    sass = subprocess.run(["cuobjdump", "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):       # tcgen05.mma / tcgen05.ld / .st / TMA (B200_PROFILING.md)
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16" not in sass                                   # no legacy mma.sync path
+
+
+def test_argument_validation_without_gpu(native_lib):
+    L = native_lib
+    assert L.memvul_abi_version() == 1
+    assert L.memvul_gemm_f16(None, None, None, None, None, 128, 100, 64, 0, None) == -1
+    assert b"N % 128" in L.memvul_last_error()
+    assert L.memvul_gemm_f16(None, None, None, None, None, 128, 128, 60, 0, None) == -1
+    assert L.memvul_attention_f16(None, None, None, 1, 128, 768, None) == -1
+    assert L.memvul_pool_match(None, 0, None, None, None, None, None, None, None, 4, 0, 768, 512, 0,
+                               None, None, None, None, None, None, None, None, 31, None) == -1
+    assert b"non-empty bank" in L.memvul_last_error()
+    assert L.memvul_pool_match(None, 0, None, None, None, None, None, None, None, 4, 3, 768, 512, 2,
+                               None, None, None, None, None, None, None, None, 1, None) == -1
+    assert L.memvul_bank_prepare(None, None, 0, 512, None, None) == -1
+    assert L.memvul_launch_count() == 0
+
+
+def test_workspace_size_formula(native_lib):
+    import torch
+    from memvul_b200 import native
+    from memvul_b200.synthetic import BERT_TINY, EMB, synthetic_state_dict
+    w = native.PackedBert(synthetic_state_dict(BERT_TINY), EMB, torch.device("cpu"))
+    M, H, I = 4 * 128, 128, 512
+    up = lambda x: (x + 1023) // 1024 * 1024
+    assert w.workspace_bytes(4, 128) == up(M * H * 2) + up(M * 3 * H * 2) + up(M * H * 2) + up(M * I * 2)
+    assert w.hidden == 128 and w.layers == 2 and w.heads == 2 and w.intermediate == 512
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly off-GPU (no oracle / CPU fallback)."""
+    import torch
+    from memvul_b200 import native
+    from memvul_b200.synthetic import BERT_TINY, build_memory_model, synthetic_ids
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model, _ = build_memory_model(BERT_TINY)
+    ids, mask, t = synthetic_ids(2, 8, vocab_size=1024)
+    with pytest.raises(native.NativeError):
+        model.forward_gold_instances({"tokens": {"token_ids": ids, "mask": mask, "type_ids": t}},
+                                     [{"type": "golden", "instance": [{"label": "x"}]}] * 2)
+    src = "".join(open(os.path.join(ROOT, "memvul_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "memvul_b200"))
+                  if f.endswith(".py"))
+    assert "oracle" not in src.replace("the CPU oracle", "").replace("CPU oracle", ""), "product code must not reference oracle/"

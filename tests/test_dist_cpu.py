@@ -1,0 +1,65 @@
+"""Multi-process (world_size 2, gloo, CPU) tests of the batch-sharding host logic."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from memvul_b200.dist import balanced_assignment, gather_match, gather_rows, shard_bounds
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 64, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_assignment_mixed_lengths():
+    g = torch.Generator().manual_seed(0)
+    lens = [int([128, 256, 512][i]) for i in torch.randint(0, 3, (512,), generator=g)]
+    buckets = balanced_assignment(lens, 8)
+    assert sorted(i for b in buckets for i in b) == list(range(512))
+    cost = lambda s: 14155776.0 * s + 3072.0 * s * s
+    loads = [sum(cost(lens[i]) for i in b) for b in buckets]
+    assert max(loads) / min(loads) < 1.02
+
+
+def _worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        G = 5
+        counts = [3, 2]                                  # ragged shards: B = 5 over 2 ranks
+        start = sum(counts[:rank])
+        b = counts[rank]
+        full_probs = torch.arange(5 * G * 2, dtype=torch.float32).view(5, G, 2) / 100.0
+        local = {"probs": full_probs[start:start + b].clone(),
+                 "best_idx": torch.tensor([(start + i) % G for i in range(b)], dtype=torch.int32),
+                 "best_probs": full_probs[start:start + b, 0].clone()}
+        out = gather_match(local, counts, full=True)
+        assert torch.equal(out["probs"], full_probs)
+        assert out["best_idx"].tolist() == [i % G for i in range(5)]
+        assert torch.equal(out["best_probs"], full_probs[:, 0])
+        red = gather_match(local, counts, full=False)
+        assert "probs" not in red and red["best_idx"].tolist() == [i % G for i in range(5)]
+        rows = gather_rows(torch.full((counts[rank], 4), float(rank)), counts)
+        assert rows.shape == (5, 4) and rows[:, 0].tolist() == [0.0, 0.0, 0.0, 1.0, 1.0]
+        eq = gather_rows(torch.full((2, 3), float(rank)), [2, 2])
+        assert eq[:, 0].tolist() == [0.0, 0.0, 1.0, 1.0]
+        with pytest.raises(ValueError):
+            gather_rows(torch.zeros(1, 2), [3, 3])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_match_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)

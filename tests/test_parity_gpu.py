@@ -1,0 +1,228 @@
+"""End-to-end GPU parity of the drop-in (ModelMemory / ModelSingle / embedder, through the C ABI) against the
+CPU oracle and the committed golden vectors.  Gates (BASELINE.json north_star):
+    |logits - oracle| <= 1e-3 absolute;  arg-max anchor and pos/neg label identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3          # north_star: "match logits within 1e-3 absolute"
+
+
+def _dev(ids, mask, tids=None):
+    d = {"token_ids": ids.cuda(), "mask": mask.cuda()}
+    d["type_ids"] = (torch.zeros_like(ids) if tids is None else tids).cuda()
+    return {"tokens": d}
+
+
+def _build_bank(model, a_ids, a_mask, chunk=128):
+    n = a_ids.shape[0]
+    for c0 in range(0, n, chunk):
+        ids, mask = a_ids[c0:c0 + chunk], a_mask[c0:c0 + chunk]
+        S = int(mask.sum(1).max())
+        model.forward_gold_instances(_dev(ids[:, :S].contiguous(), mask[:, :S].contiguous()),
+                                     [{"type": "golden", "instance": [{"label": f"CWE-{c0 + i}"}]} for i in range(ids.shape[0])])
+
+
+def _meta(n, kind="unlabel"):
+    return [{"type": kind, "instance": [{"label": "neg" if i % 3 else f"CWE-{i}", "Issue_Url": f"url/{i}"}]} for i in range(n)]
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "tiny_same1", "base_small"])
+def test_model_memory_matches_golden(name):
+    from memvul_b200.synthetic import build_memory_model
+    from oracle.make_golden import CASES
+    shape, lens, S, alens, same = CASES[name]
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    model, _ = build_memory_model(shape, same_first=(same == 0), device="cuda")
+    assert model._same_idx == same
+    with torch.no_grad():
+        _build_bank(model, torch.from_numpy(z["anchor_ids"]), torch.from_numpy(z["anchor_mask"]))
+        out = model(sample1=_dev(torch.from_numpy(z["ids"]), torch.from_numpy(z["mask"])),
+                    label=torch.zeros(len(lens), dtype=torch.int64, device="cuda"), metadata=_meta(len(lens)))
+    dev = out["native"]["device"]
+    assert float((model._golden_instances_embeddings.cpu() - torch.from_numpy(z["bank"])).abs().max()) < TOL
+    assert float((dev["u"].cpu() - torch.from_numpy(z["u"])).abs().max()) < TOL
+    assert float((dev["logits"].cpu() - torch.from_numpy(z["logits"])).abs().max()) < TOL
+    p = np.asarray(out["probs"].tolist(), dtype=np.float32)
+    assert p.shape == z["p"].shape and np.abs(p - z["p"]).max() < TOL
+    # arg-max anchor identical wherever the oracle's top-2 gap exceeds the tolerance; report the margin
+    ps = z["p"][:, :, same]
+    top2 = np.sort(ps, axis=1)[:, -2:] if ps.shape[1] > 1 else np.stack([ps[:, 0] - 1, ps[:, 0]], 1)
+    clear = (top2[:, 1] - top2[:, 0]) > 2 * TOL
+    got = np.asarray(out["native"]["best_idx"].tolist())
+    assert (got[clear] == z["best_idx"][clear]).all(), (got, z["best_idx"], top2)
+    for thres in (0.5, 0.55):
+        vote_ref, vote_got = ps.max(1), p[:, :, same].max(1)
+        safe = np.abs(vote_ref - thres) > TOL
+        assert ((vote_got >= thres) == (vote_ref >= thres))[safe].all()
+    rows = model.make_output_human_readable(out)
+    assert len(rows) == len(lens) and set(rows[0]) == {"Issue_Url", "label", "predict"} and len(rows[0]["predict"]) == len(alens)
+    json.dumps(rows)
+
+
+def test_bert_base_batch_against_oracle_with_labels():
+    """bert-base, 8 ragged issue reports x 129 anchors (the real memory size), oracle computed on CPU in seconds."""
+    from memvul_b200.synthetic import BERT_BASE, build_memory_model, synthetic_ids
+    from oracle import memvul_oracle as O
+    model, sd = build_memory_model(BERT_BASE, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    alens = torch.randint(8, 65, (129,), generator=g).tolist()
+    a_ids, a_mask, _ = synthetic_ids(129, 64, lens=alens, seed=21)
+    lens = [128, 100, 64, 17, 128, 90, 2, 77]
+    ids, mask, tids = synthetic_ids(8, 128, lens=lens, seed=22)
+    with torch.no_grad():
+        _build_bank(model, a_ids, a_mask)                      # 128 + 1 chunks, as predict_memory.py:81-83
+        out = model(sample1=_dev(ids, mask, tids), label=torch.ones(8, dtype=torch.int64, device="cuda"), metadata=_meta(8))
+        bank = O.build_bank(sd, [(a_ids[i][a_mask[i]], a_mask[i][a_mask[i]]) for i in range(129)])
+        ref = O.memory_forward(sd, ids, mask, tids, bank, model._same_idx)
+    dev = out["native"]["device"]
+    err = float((dev["logits"].cpu() - ref["logits"]).abs().max())
+    assert err < TOL, err
+    ps = ref["p"][:, :, model._same_idx]
+    top2 = ps.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2 * TOL
+    got = torch.tensor(out["native"]["best_idx"].tolist())
+    assert torch.equal(got[clear], ref["best_idx"][clear])
+    vote_got = torch.tensor(out["probs"].tolist())[:, :, model._same_idx].max(1).values
+    vote_ref, _ = O.vote_labels(ps, 0.5)
+    safe = (vote_ref - 0.5).abs() > TOL
+    assert torch.equal((vote_got >= 0.5)[safe], (vote_ref >= 0.5)[safe])
+    print(f"logits max err {err:.2e}; min vote margin {float((vote_ref - 0.5).abs().min()):.3e}; clear argmax rows {int(clear.sum())}/8")
+    m = model.get_metrics(reset=True)
+    assert 0.0 <= m["accuracy"] <= 1.0 and "s_thres" in m and "same_f1-score" in m
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] size (bert-base, S=512, B=64, G=129): size-independent properties + an oracle spot check."""
+    from memvul_b200.synthetic import BERT_BASE, build_memory_model, synthetic_ids
+    from oracle import memvul_oracle as O
+    model, sd = build_memory_model(BERT_BASE, device="cuda")
+    g = torch.Generator().manual_seed(9)
+    alens = torch.randint(16, 129, (129,), generator=g).tolist()
+    a_ids, a_mask, _ = synthetic_ids(129, 128, lens=alens, seed=31)
+    lens = torch.randint(300, 513, (64,), generator=g).tolist()
+    lens[0], lens[1] = 512, 512
+    ids, mask, tids = synthetic_ids(64, 512, lens=lens, seed=32)
+    ids[1], mask[1] = ids[0], mask[0]                               # duplicate rows -> identical outputs
+    with torch.no_grad():
+        _build_bank(model, a_ids, a_mask)
+        r1 = model.match_batch(_dev(ids, mask, tids))
+        l1, p1, b1 = r1["logits"].clone(), r1["probs"].clone(), r1["best_idx"].clone()
+        perm = torch.randperm(64, generator=g)
+        r2 = model.match_batch(_dev(ids[perm].contiguous(), mask[perm].contiguous(), tids))
+        assert torch.equal(r2["logits"], l1[perm.cuda()]), "batch order must not change any sample's result"
+        assert torch.equal(l1[0], l1[1]) and int(b1[0]) == int(b1[1])
+        assert torch.equal(b1.long(), p1[:, :, model._same_idx].argmax(1))
+        assert float((p1.sum(-1) - 1).abs().max()) < 1e-6
+        # shrinking the padding of a short batch does not change its rows
+        short = [i for i in range(64) if lens[i] <= 384][:8]
+        if short:
+            S2 = max(lens[i] for i in short)
+            ra = model.match_batch(_dev(ids[short].contiguous(), mask[short].contiguous()))["logits"].clone()
+            rb = model.match_batch(_dev(ids[short][:, :S2].contiguous(), mask[short][:, :S2].contiguous()))["logits"]
+            assert float((ra - rb).abs().max()) < 1e-5
+        # oracle spot check on 3 of the 64 full-size rows
+        pick = [0, 7, 33]
+        bank = model._golden_instances_embeddings.cpu()
+        ref = O.memory_forward(sd, ids[pick], mask[pick], tids[pick], bank, model._same_idx)
+    assert float((l1[pick].cpu() - ref["logits"]).abs().max()) < TOL
+
+
+def test_embedder_interface_and_errors():
+    from memvul_b200 import native
+    from memvul_b200.synthetic import BERT_TINY, build_memory_model, synthetic_ids
+    from oracle import memvul_oracle as O
+    model, sd = build_memory_model(BERT_TINY, device="cuda")
+    emb = model._text_field_embedder
+    ids, mask, tids = synthetic_ids(3, 33, lens=[33, 4, 20], vocab_size=1024)
+    tids[:, 10:] = 1
+    tids = tids * mask
+    with torch.no_grad():
+        hid = emb(_dev(ids, mask, tids))
+        ref = O.embedder_forward(sd, ids, mask, tids, O.BERT_TINY)
+    assert hid.shape == (3, 33, 128) and emb.get_output_dim() == 128
+    assert float((hid.cpu() - ref)[mask].abs().max()) < 5e-3
+    bad = mask.clone(); bad[1, 20] = True
+    with torch.no_grad(), pytest.raises(ValueError):
+        model.forward_gold_instances(_dev(ids, bad), _meta(3, "golden"))
+    with pytest.raises(RuntimeError):
+        model(sample1=_dev(ids, mask), metadata=_meta(3))               # empty memory
+    with pytest.raises(ValueError):
+        emb.embedder("tokens")(ids.cuda(), mask.cuda()[:, :5])
+    # weights changed in place -> packed fp16 copy is rebuilt
+    with torch.no_grad():
+        h0 = emb(_dev(ids, mask)).clone()
+        model.state_dict()[O.EMB + "embeddings.LayerNorm.bias"].add_(0.5)
+        assert not torch.allclose(emb(_dev(ids, mask)), h0)
+
+
+def test_model_single_matches_oracle():
+    from memvul_b200.custom_PTM_embedder import PretrainedTransformerEmbedder
+    from memvul_b200.model_single import ModelSingle
+    from memvul_b200.modules import BasicTextFieldEmbedder
+    from memvul_b200.registrable import Vocabulary
+    from memvul_b200.synthetic import BERT_TINY, config_lite, load_into, synthetic_ids, synthetic_state_dict
+    from oracle import memvul_oracle as O
+    sd = synthetic_state_dict(BERT_TINY, model="single")
+    emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(BERT_TINY))
+    model = ModelSingle(Vocabulary({"class_labels": ["neg", "pos"]}), BasicTextFieldEmbedder({"tokens": emb}))
+    load_into(model, sd)
+    model.eval().cuda()
+    ids, mask, tids = synthetic_ids(4, 128, lens=[128, 9, 64, 100], vocab_size=1024)   # config C1 shape: B=4, S=128
+    label = torch.tensor([0, 1, 1, 0])
+    with torch.no_grad():
+        out = model(_dev(ids, mask, tids), label=label.cuda(),
+                    metadata=[{"instance": {"Issue_Url": f"u{i}", "label": "neg"}} for i in range(4)])
+        ref = O.single_forward(sd, ids, mask, tids, O.BERT_TINY)
+    assert float((torch.tensor(out["probs"]) - ref["probs"]).abs().max()) < TOL
+    assert float(out["loss"]) == pytest.approx(float(torch.nn.functional.cross_entropy(ref["logits"], label)), abs=TOL)
+    rows = model.make_output_human_readable(out)
+    assert rows[0].keys() == {"Issue_Url", "label", "predict", "prob"}
+
+
+def test_predict_driver_end_to_end(tmp_path_factory):
+    """predict_memory.test_siamese flow on a toy archive: archive -> bank (128+rest) -> batches -> JSON lines -> cal_metrics."""
+    import tarfile
+    from memvul_b200 import predict_memory as PM
+    from memvul_b200.synthetic import BERT_TINY, synthetic_state_dict
+    from tests.test_host import TOY_VOCAB
+    d = tmp_path_factory.mktemp("arch")
+    vocab_file = d / "vocab.txt"
+    vocab_file.write_text("\n".join(TOY_VOCAB) + "\n")
+    (d / "vocabulary").mkdir()
+    (d / "vocabulary" / "labels.txt").write_text("same\ndiff\n")
+    tok = {"type": "pretrained_transformer", "model_name": str(vocab_file), "add_special_tokens": True, "max_length": 32}
+    cve = d / "CVE_dict.json"
+    cve.write_text(json.dumps({f"CVE-{i}": {"CWE_ID": f"CWE-{i % 3}"} for i in range(20)}))
+    cfg = {"dataset_reader": {"type": "reader_memory", "tokenizer": tok, "cve_dict_path": str(cve)},
+           "validation_dataset_reader": {"type": "reader_memory", "tokenizer": tok},
+           "model": {"type": "model_memory", "device": "cuda:0", "text_field_embedder": {"token_embedders": {"tokens": {
+               "type": "custom_pretrained_transformer", "model_name": "bert-base-uncased", "pretrained_model_path": "",
+               "transformer_kwargs": {"vocab_size": 1024, "hidden_size": 128, "num_hidden_layers": 2,
+                                      "num_attention_heads": 2, "intermediate_size": 512}}}}},
+           "validation_data_loader": {"batch_size": 4, "shuffle": False}}
+    (d / "config.json").write_text(json.dumps(cfg))
+    torch.save(synthetic_state_dict(BERT_TINY), d / "weights.th")
+    with tarfile.open(d / "model.tar.gz", "w:gz") as t:
+        for n in ("config.json", "weights.th", "vocabulary"):
+            t.add(d / n, arcname=n)
+    words = ["buffer", "overflow", "parser", "sql", "injection", "crash", "null", "heap", "free", "fix"]
+    (d / "CWE_anchor_golden_project.json").write_text(json.dumps({f"CWE-{i}": " ".join(words[i:i + 3]) for i in range(3)}))
+    rows = [{"Issue_Url": f"u{i}", "Issue_Title": words[i % 10], "Issue_Body": " ".join(words[(i * 3) % 7:(i * 3) % 7 + 4]),
+             "Security_Issue_Full": int(i % 4 == 0), "CVE_ID": f"CVE-{i}"} for i in range(11)]
+    (d / "test_project.json").write_text(json.dumps(rows))
+    res = d / "out_result.json"
+    metrics = PM.test_siamese(str(d / "model.tar.gz"), str(d / "test_project.json"), str(d / "CWE_anchor_golden_project.json"),
+                              predictions_output_file=str(res), batch_size=4, cuda_device=0)
+    lines = [json.loads(l) for l in res.read_text().splitlines()]
+    assert [len(l) for l in lines] == [4, 4, 3]
+    assert [r["Issue_Url"] for r in lines[0]][:3] == ["u8", "u4", "u0"]          # positives first (reversed groups)
+    assert all(set(r["predict"]) == {"CWE-0", "CWE-1", "CWE-2"} for l in lines for r in l)
+    assert "s_f1-score" in metrics and "accuracy" in metrics
+    m = PM.cal_metrics(str(res), thres=0.5)
+    assert m["TP"] + m["FN"] == 3 and m["TN"] + m["FP"] == 8
