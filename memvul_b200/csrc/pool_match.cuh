@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p
   if (p.phase_mask & PM_POOL) {
     phase_sync();
     dense_rows_phase<0>(p.cls, p.cls_stride, p.wp, p.bp, p.pooled, p.B, p.H, p.H, gwarp, nwarps, lane);
-    for (int b = gtid; b < p.B; b += nthreads) p.best_key[b] = 0ull;
+    if (p.best_key)
+      for (int b = gtid; b < p.B; b += nthreads) p.best_key[b] = 0ull;
   }
   if (p.phase_mask & PM_HEADER) {
     phase_sync();

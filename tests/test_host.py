@@ -17,9 +17,7 @@ from memvul_b200.registrable import DatasetReader, Metric, Model, TokenEmbedder,
 from memvul_b200.synthetic import BERT_TINY, build_memory_model, synthetic_state_dict
 from memvul_b200.tokenizer import WordPieceTokenizer
 
-TOY_VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "buffer", "over", "##flow", "in", "the", "parser", ".", ",",
-             "sql", "injection", "##s", "crash", "when", "url", "##tag", "is", "null", "a", "b", "fix", "##ed", "!", "use",
-             "after", "free", "-", "heap", "cafe", "x", "##y", "##z"]
+from toy_vocab import TOY_VOCAB  # noqa: E402
 
 
 @pytest.fixture()

@@ -190,7 +190,7 @@ def test_predict_driver_end_to_end(tmp_path_factory):
     import tarfile
     from memvul_b200 import predict_memory as PM
     from memvul_b200.synthetic import BERT_TINY, synthetic_state_dict
-    from tests.test_host import TOY_VOCAB
+    from toy_vocab import TOY_VOCAB
     d = tmp_path_factory.mktemp("arch")
     vocab_file = d / "vocab.txt"
     vocab_file.write_text("\n".join(TOY_VOCAB) + "\n")
