@@ -15,28 +15,30 @@
 // Warps 0-3 : softmax (one query row per thread; S read from TMEM, P written to smem as the
 //             fp16 A operand of the second MMA, running max / sum in fp32, O rescaled in TMEM)
 // Warp 4    : lane 0 issues the TMA loads and both tcgen05.mma streams.
-// TMEM      : S double buffer 2 x 128 cols, O 64 cols.   Key length <= 512 (4 blocks of 128).
+// Footprint : 112 KB smem (Q 16 K, 2-stage K/V ring 64 K, P 32 K) and 256 TMEM columns (S 128, O 64) so that
+//             TWO CTAs are resident per SM: one CTA's softmax overlaps the other's MMAs/TMA.
+//             Key length <= 512 (4 blocks of 128).
 #pragma once
 #include "ptx.cuh"
 
 namespace mv {
 
 struct AttnCfg {
-  static constexpr int BQ = 128, BKV = 128, DH = 64, MAX_KB = 4;
+  static constexpr int BQ = 128, BKV = 128, DH = 64, MAX_KB = 4, KV_STAGES = 2;
   static constexpr int TILE_BYTES = 128 * 64 * 2;          // 16 KB: one {64 x 128} fp16 box
   static constexpr int P_BYTES = 2 * TILE_BYTES;           // 128 x 128 fp16 = two K-chunks
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;         // 114,944 B: two CTAs fit in 228 KB
   static constexpr int THREADS = 160;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int TM_S = 0, TM_O = 256;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int TM_S = 0, TM_O = 128;
 };
 
-__global__ void __launch_bounds__(AttnCfg::THREADS, 1)
+__global__ void __launch_bounds__(AttnCfg::THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int* __restrict__ lens,
                          __half* __restrict__ ctx, int S, int H) {
   using C = AttnCfg;
@@ -57,8 +59,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
     return;
   }
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];        // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* k_full = bars + 1;             // [4]
@@ -94,25 +95,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
 
   if (warp_idx == 4) {
     if (lane == 0) {
-      // ---------------- TMA: Q, then K/V blocks in consumption order ----------------
+      // ---------------- TMA: Q, then the first KV_STAGES K/V blocks ----------------
       const int row_q = static_cast<int>(row_base) + q0;
-      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
-      tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_q, kEvictFirst);
-      for (int j = 0; j < nkb; ++j) {
+      auto load_kv = [&](int j) {
+        const int st = j % C::KV_STAGES;
         const int row_k = static_cast<int>(row_base) + j * C::BKV;
         mbar_arrive_expect_tx(&k_full[j], C::TILE_BYTES);
-        tma_load_2d(smem + C::OFF_K + j * C::TILE_BYTES, &tmap_qkv, &k_full[j], H + h * C::DH, row_k, kEvictLast);
+        tma_load_2d(smem + C::OFF_K + st * C::TILE_BYTES, &tmap_qkv, &k_full[j], H + h * C::DH, row_k, kEvictLast);
         mbar_arrive_expect_tx(&v_full[j], C::TILE_BYTES);
-        tma_load_2d(smem + C::OFF_V + j * C::TILE_BYTES, &tmap_qkv, &v_full[j], 2 * H + h * C::DH, row_k,
-                    kEvictLast);
-      }
+        tma_load_2d(smem + C::OFF_V + st * C::TILE_BYTES, &tmap_qkv, &v_full[j], 2 * H + h * C::DH, row_k, kEvictLast);
+      };
+      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+      tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_q, kEvictFirst);
+      for (int j = 0; j < nkb && j < C::KV_STAGES; ++j) load_kv(j);
       // ---------------- MMA issue ----------------
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);   // S = Q K^T   (both K-major)
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);     // O += P V    (V is N-major)
       const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + C::OFF_Q));
       auto issue_qk = [&](int j) {
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + j * C::TILE_BYTES));
-        const uint32_t d = tmem_base + C::TM_S + static_cast<uint32_t>((j & 1) * 128);
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + (j % C::KV_STAGES) * C::TILE_BYTES));
+        const uint32_t d = tmem_base + C::TM_S;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
@@ -124,17 +126,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
       tc_fence_after();
       issue_qk(0);
       for (int j = 0; j < nkb; ++j) {
+        mbar_wait(&p_full[j], 0);          // P_j in smem, S drained (single S buffer), O rescaled
         if (j + 1 < nkb) {
-          // S buffer (j+1)&1 was last read for block j-1, whose p_full we already waited on.
           mbar_wait(&k_full[j + 1], 0);
           tc_fence_after();
-          issue_qk(j + 1);
+          issue_qk(j + 1);                 // overlaps the softmax of block j+1 with P_j V_j below
         }
-        mbar_wait(&p_full[j], 0);
         mbar_wait(&v_full[j], 0);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + C::OFF_P + (j & 1) * C::P_BYTES);
-        const uint32_t v_addr = smem_u32(smem + C::OFF_V + j * C::TILE_BYTES);
+        const uint32_t p_addr = smem_u32(smem + C::OFF_P);
+        const uint32_t v_addr = smem_u32(smem + C::OFF_V + (j % C::KV_STAGES) * C::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // A = P: K-major, two 64-wide K chunks of 16 KB, 32 B per K=16 step inside a chunk.
@@ -145,6 +146,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
           umma_f16_ss(tmem_base + C::TM_O, a_desc, b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[j]);
+        if (j + C::KV_STAGES < nkb) {      // recycle this K/V stage once Q K_j^T and P_j V_j have retired
+          mbar_wait(&pv_done[j], 0);
+          load_kv(j + C::KV_STAGES);
+        }
       }
     }
   } else {
@@ -157,7 +162,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
       mbar_wait(&s_full[j], 0);
       tc_fence_after();
       uint32_t s[4][32];
-      const uint32_t s_addr = tmem_base + lane_addr + C::TM_S + static_cast<uint32_t>((j & 1) * 128);
+      const uint32_t s_addr = tmem_base + lane_addr + C::TM_S;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_addr + cc * 32, s[cc]);
       tmem_wait_ld();
@@ -174,7 +179,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
       const float m_new = fmaxf(m_run, mx);
       const float mc = m_new * c;
       float l_blk = 0.f;
-      uint8_t* p_row = smem + C::OFF_P + (j & 1) * C::P_BYTES + r * 128;
+      if (j > 0) {
+        mbar_wait(&pv_done[j - 1], 0);       // O holds blocks 0..j-1 and the single P buffer is free again
+        tc_fence_after();
+      }
+      uint8_t* p_row = smem + C::OFF_P + r * 128;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
@@ -197,8 +206,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
       }
       const float alpha = exp2f((m_run - m_new) * c);          // 0 on the first block (m_run = -inf)
       if (j > 0) {
-        mbar_wait(&pv_done[j - 1], 0);                         // O holds blocks 0..j-1; P[(j-1)&1] is free again
-        tc_fence_after();
         if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {

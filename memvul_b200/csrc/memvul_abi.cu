@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -14,6 +15,7 @@
 #include "../../include/memvul_b200.h"
 #include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2cta.cuh"
 #include "pool_match.cuh"
 #include "rowwise.cuh"
 
@@ -123,9 +125,10 @@ EncodeTiledFn encode_fn() {
 struct MapKey {
   const void* base;
   uint64_t rows, cols, ld;
-  uint32_t box_rows;
+  uint32_t box_rows, box_cols, elem_bytes;
   bool operator==(const MapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && elem_bytes == o.elem_bytes;
   }
 };
 struct MapKeyHash {
@@ -135,14 +138,17 @@ struct MapKeyHash {
     h = h * 1315423911u ^ k.cols;
     h = h * 1315423911u ^ k.ld;
     h = h * 1315423911u ^ k.box_rows;
+    h = h * 1315423911u ^ (k.box_cols * 8u + k.elem_bytes);
     return h;
   }
 };
-// fp16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}, SWIZZLE_128B.
-int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+// Row-major [rows, cols] matrix of fp16 (elem_bytes 2) or fp32 (4) with leading dimension ld (elements);
+// box = {box_cols, box_rows} with box_cols * elem_bytes == 128 B, SWIZZLE_128B.
+int make_map(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+             uint32_t elem_bytes, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{base, rows, cols, ld, box_rows};
+  MapKey key{base, rows, cols, ld, box_rows, box_cols, elem_bytes};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -153,14 +159,16 @@ int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, ui
   }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MEMVUL_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u))
-    return fail(MEMVUL_E_INVALID, "TMA operand must be 16-byte aligned (ptr=%p ld=%llu)", base, (unsigned long long)ld);
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * elem_bytes) & 15u) || box_cols * elem_bytes != 128)
+    return fail(MEMVUL_E_INVALID, "TMA operand must be 16-byte aligned with 128-byte box rows (ptr=%p ld=%llu)", base,
+                (unsigned long long)ld);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t gstride[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MEMVUL_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -171,6 +179,9 @@ int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, ui
   }
   *out = m;
   return MEMVUL_OK;
+}
+int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+  return make_map(base, rows, cols, ld, box_rows, 64, 2, out);
 }
 
 // ------------------------------------------------------------------ launchers
@@ -203,6 +214,45 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M
   return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
+
+template <int EPI>
+int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
+                     const float* resid, void* out, int sms, cudaStream_t st) {
+  using Cfg = mv::Gemm2Cfg<EPI>;
+  auto kern = mv::gemm_f16_tcgen05_2cta_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  static const bool nostore = getenv("MEMVUL_GEMM_NOSTORE") != nullptr;      // experiment: time the main loop alone
+  CUtensorMap tout, tres;
+  if (Cfg::RESID) {
+    if (int rc = make_map(out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tout)) return rc;
+    if (int rc = make_map(resid, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tres)) return rc;
+  } else {
+    if (int rc = make_map(out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2, &tout)) return rc;
+    tres = tout;
+  }
+  const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / Cfg::BN);
+  int clusters = sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  LaunchScope ls(g_cls, st);
+  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias, nostore ? 0 : 1);   // __cluster_dims__(2,1,1)
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int launch_gemm_2cta_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
+                         const float* resid, void* out, int sms, cudaStream_t st) {
+  switch (epi) {
+    case MEMVUL_EPI_BIAS_F16: return launch_gemm_2cta<mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm_2cta<mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm_2cta<mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st);
+  }
+  return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
 int gemm_impl(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
               int epi, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(MEMVUL_E_INVALID, "GEMM with empty shape M=%d N=%d K=%d", M, N, K);
@@ -213,6 +263,14 @@ int gemm_impl(const void* a, const void* w, const float* bias, const float* resi
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int tiles_m = (M + 127) / 128;
+  // CTA-pair kernel (256 x 256 tiles) once there is at least one tile per SM pair; MEMVUL_GEMM_MODE=1cta disables it.
+  static const bool allow_2cta = [] { const char* e = getenv("MEMVUL_GEMM_MODE"); return !(e && strcmp(e, "1cta") == 0); }();
+  if (allow_2cta && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= di.sms / 2) {
+    CUtensorMap ta2, tb2;
+    if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta2)) return rc;
+    if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, &tb2)) return rc;
+    return launch_gemm_2cta_epi(epi, ta2, tb2, M, N, K, bias, resid, out, di.sms, st);
+  }
   const bool bn256 = (N % 256 == 0) && (tiles_m * (N / 256) >= di.sms);
   const int BN = bn256 ? 256 : 128;
   CUtensorMap ta, tb;
