@@ -34,6 +34,9 @@ enum {
   MEMVUL_E_WORKSPACE = -3  /* workspace too small              */
 };
 
+/* memvul_encoder_forward flags */
+enum { MEMVUL_ENC_CLS_ONLY = 1 };
+
 /* GEMM epilogues (memvul_gemm_f16) */
 enum {
   MEMVUL_EPI_BIAS_F16 = 0,       /* out fp16 = A W^T + bias                    */
@@ -76,10 +79,13 @@ size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S
  *   token_ids [B,S] int64; type_ids [B,S] int64 or NULL (all zero, custom_PTM_embedder.py:199-202);
  *   lens [B] int32 = number of unmasked (prefix) tokens per sequence, 1 <= len <= S;
  *   hidden_out [B*S, H] fp32 = last_hidden_state (rows of padded tokens are unspecified).
+ * flags: MEMVUL_ENC_CLS_ONLY -- only hidden_out[b*S + 0] (the [CLS] row BertPooler reads, model_memory.py:99) is the
+ *   last layer's output; the last layer then runs its attention on the first query tile and its output projection /
+ *   FFN / LayerNorms on B rows instead of B*S (identical arithmetic per row; ~1/12 of the encoder's work saved).
  * Supported: H in {128, 768} (H % 128 == 0, head_dim == 64), S <= 512, S <= max_pos. */
 int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
                            const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           size_t workspace_bytes, int flags, void* stream);
 
 /* bool mask [B,S] (1 byte each, AllenNLP `mask`) -> lens[B]; *bad_flag (device int32) is set to 1 if a
  * mask is not a non-empty prefix mask.  (custom_PTM_embedder.py:215-216 consumes the mask.) */

@@ -280,7 +280,8 @@ int gemm_impl(const void* a, const void* w, const float* bias, const float* resi
                : launch_gemm_epi<128>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st);
 }
 
-int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st) {
+int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st,
+                   bool first_tile_only = false) {
   if (B <= 0 || S <= 0 || S > 512) return fail(MEMVUL_E_INVALID, "attention needs 1 <= S <= 512 (B=%d S=%d)", B, S);
   if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
   DeviceInfo di;
@@ -293,7 +294,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
                                   mv::AttnCfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((S + 127) / 128, H / 64, B);
+  dim3 grid(first_tile_only ? 1 : (S + 127) / 128, H / 64, B);
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
       tq, lens, reinterpret_cast<__half*>(ctx), S, H);
@@ -302,14 +303,15 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
 }
 
 int layernorm_impl(const float* y, const float* g, const float* b, float eps, float* x32, void* x16, int M, int H,
-                   cudaStream_t st) {
+                   cudaStream_t st, long long x32_stride = 0) {
   if (M <= 0) return fail(MEMVUL_E_INVALID, "layernorm with M=%d", M);
+  if (x32_stride == 0) x32_stride = H;
   const int blocks = (M + 7) / 8;
   LaunchScope ls(KC_LAYERNORM, st);
   if (H == 768)
-    mv::layernorm_rows_kernel<6><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, reinterpret_cast<__half*>(x16), M);
+    mv::layernorm_rows_kernel<6><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, x32_stride, reinterpret_cast<__half*>(x16), M);
   else if (H == 128)
-    mv::layernorm_rows_kernel<1><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, reinterpret_cast<__half*>(x16), M);
+    mv::layernorm_rows_kernel<1><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, x32_stride, reinterpret_cast<__half*>(x16), M);
   else
     return fail(MEMVUL_E_INVALID, "layernorm supports H in {128, 768}, got %d", H);
   CUDA_TRY(cudaGetLastError());
@@ -355,6 +357,7 @@ __global__ void mask_to_lens_kernel(const uint8_t* __restrict__ mask, int B, int
 
 struct Workspace {
   __half* x16; __half* qkv; __half* ctx; __half* ffn;
+  float* x32_cls; __half* x16_cls; __half* ctx_cls; __half* ffn_cls;     // [B, *] rows of the CLS-only last layer
   size_t bytes;
 };
 Workspace carve(const memvul_bert_weights* w, int B, int S, void* base) {
@@ -367,6 +370,11 @@ Workspace carve(const memvul_bert_weights* w, int B, int S, void* base) {
   ws.qkv = reinterpret_cast<__half*>(p + off); off += up(M * 3 * H * 2);
   ws.ctx = reinterpret_cast<__half*>(p + off); off += up(M * H * 2);
   ws.ffn = reinterpret_cast<__half*>(p + off); off += up(M * I * 2);
+  const size_t Bp = static_cast<size_t>(B);
+  ws.x32_cls = reinterpret_cast<float*>(p + off); off += up(Bp * H * 4);
+  ws.x16_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * H * 2);
+  ws.ctx_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * H * 2);
+  ws.ffn_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * I * 2);
   ws.bytes = off;
   return ws;
 }
@@ -425,7 +433,7 @@ int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_
 
 int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
                            const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           size_t workspace_bytes, int flags, void* stream) {
   if (int rc = check_weights(w)) return rc;
   if (!token_ids || !lens || !hidden_out || !workspace) return fail(MEMVUL_E_INVALID, "encoder null pointer");
   if (B <= 0 || S <= 0 || S > 512 || S > w->max_pos)
@@ -437,8 +445,29 @@ int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_id
   const int M = B * S, H = w->hidden, I = w->intermediate;
   float* x32 = hidden_out;
   if (int rc = embed_impl(w, token_ids, type_ids, B, S, x32, ws.x16, st)) return rc;
+  const bool cls_only = (flags & MEMVUL_ENC_CLS_ONLY) != 0;
   for (int l = 0; l < w->layers; ++l) {
     const memvul_bert_layer& L = w->layer[l];
+    if (cls_only && l == w->layers - 1) {
+      // Last layer, [CLS]-only tail: keys/values need every row, but only query row 0 of each sequence is consumed
+      // downstream, so attention runs on the first query tile and everything after it on B gathered rows.
+      { ClassScope cs(KC_GEMM_QKV);
+      if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
+      if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st, /*first_tile_only=*/true)) return rc;
+      { LaunchScope ls(KC_OTHER, st);
+        mv::gather_cls_rows_kernel<<<B, 192, 0, st>>>(x32, ws.ctx, ws.x32_cls, ws.ctx_cls, B, S, H);
+        CUDA_TRY(cudaGetLastError()); }
+      { ClassScope cs(KC_GEMM_ATTN_OUT);
+      if (int rc = gemm_impl(ws.ctx_cls, L.w_ao, L.b_ao, ws.x32_cls, ws.x32_cls, B, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
+      if (int rc = layernorm_impl(ws.x32_cls, L.ln1_g, L.ln1_b, w->ln_eps, ws.x32_cls, ws.x16_cls, B, H, st)) return rc;
+      { ClassScope cs(KC_GEMM_FFN_UP);
+      if (int rc = gemm_impl(ws.x16_cls, L.w_ff1, L.b_ff1, nullptr, ws.ffn_cls, B, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc; }
+      { ClassScope cs(KC_GEMM_FFN_DOWN);
+      if (int rc = gemm_impl(ws.ffn_cls, L.w_ff2, L.b_ff2, ws.x32_cls, ws.x32_cls, B, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
+      // final LayerNorm scatters row b into hidden_out[b*S] (the [CLS] slot); other rows keep layer L-1 values
+      if (int rc = layernorm_impl(ws.x32_cls, L.ln2_g, L.ln2_b, w->ln_eps, x32, nullptr, B, H, st, (long long)S * H)) return rc;
+      break;
+    }
     { ClassScope cs(KC_GEMM_QKV);
     if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
     if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st)) return rc;

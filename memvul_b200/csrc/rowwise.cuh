@@ -46,10 +46,12 @@ __device__ __forceinline__ void ln_store(float4 (&v)[NV], const float* __restric
 }
 
 // y [M,H] fp32 (pre-LN residual sum)  ->  x32 [M,H] fp32, x16 [M,H] fp16.   In-place (x32 == y) is fine.
+// x32_stride: elements between consecutive output rows of x32 (H for a dense matrix; S*H scatters row b to the
+// [CLS] slot of sequence b in a [B,S,H] tensor).
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* y, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, float* x32,
-                                                             __half* __restrict__ x16, int M) {
+                                                             long long x32_stride, __half* __restrict__ x16, int M) {
   constexpr int H = NV * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -58,8 +60,21 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* y, con
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
-  ln_store<NV>(v, gamma, beta, eps, x32 ? x32 + static_cast<size_t>(row) * H : nullptr,
+  ln_store<NV>(v, gamma, beta, eps, x32 ? x32 + static_cast<size_t>(row) * x32_stride : nullptr,
                x16 ? x16 + static_cast<size_t>(row) * H : nullptr, lane);
+}
+
+// Gather one row per sequence (row b*S of a [B*S, H] matrix) into dense [B, H] matrices: the [CLS] rows that the last
+// encoder layer's output projection / FFN actually need (BertPooler reads hidden[:,0] only, model_memory.py:99).
+__global__ void __launch_bounds__(256) gather_cls_rows_kernel(const float* __restrict__ x32, const __half* __restrict__ c16,
+                                                              float* __restrict__ x32_cls, __half* __restrict__ c16_cls,
+                                                              int B, int S, int H) {
+  const int b = blockIdx.x;
+  const size_t src = static_cast<size_t>(b) * S * H, dst = static_cast<size_t>(b) * H;
+  for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
+    *reinterpret_cast<float4*>(x32_cls + dst + i) = *reinterpret_cast<const float4*>(x32 + src + i);
+    *reinterpret_cast<uint2*>(c16_cls + dst + i) = *reinterpret_cast<const uint2*>(c16 + src + i);
+  }
 }
 
 // K1: LN(word[ids] + pos[s] + type[tt]).  ids / type_ids are int64 [B*S] as AllenNLP's

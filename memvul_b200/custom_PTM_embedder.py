@@ -95,17 +95,18 @@ class PretrainedTransformerEmbedder(TokenEmbedder):
         return self._workspace
 
     def encode(self, token_ids: torch.Tensor, lens: torch.Tensor, type_ids: Optional[torch.Tensor] = None,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[B,S] ids + per-sequence lengths -> fp32 [B,S,H]; asynchronous on the current stream."""
+               out: Optional[torch.Tensor] = None, cls_only: bool = False) -> torch.Tensor:
+        """[B,S] ids + per-sequence lengths -> fp32 [B,S,H]; asynchronous on the current stream.
+        ``cls_only``: only ``[:, 0]`` is the final layer's output (enough for BertPooler)."""
         B, S = token_ids.shape
         return native.encoder_forward(self.packed(), token_ids.contiguous(), lens,
                                       None if type_ids is None else type_ids.contiguous(),
-                                      self.workspace(B, S, token_ids.device), out)
+                                      self.workspace(B, S, token_ids.device), out, cls_only=cls_only)
 
     # ------------------------------------------------------------------ reference interface
     def forward(self, token_ids: torch.LongTensor, mask: torch.BoolTensor,
                 type_ids: Optional[torch.LongTensor] = None,
-                segment_concat_mask: Optional[torch.BoolTensor] = None) -> torch.Tensor:
+                segment_concat_mask: Optional[torch.BoolTensor] = None, *, cls_only: bool = False) -> torch.Tensor:
         if self._max_length is not None and token_ids.size(1) > self._max_length:
             raise NotImplementedError("fold/unfold of long sequences (custom_PTM_embedder.py:244-381) is unreachable "
                                       "in the MemVul configs and not implemented")
@@ -114,7 +115,7 @@ class PretrainedTransformerEmbedder(TokenEmbedder):
         if type_ids is not None and token_ids.shape != type_ids.shape:
             raise ValueError("token_ids and type_ids must have the same shape")       # :205-206
         lens, bad = native.mask_to_lens(mask.contiguous())
-        hidden = self.encode(token_ids, lens, type_ids)
+        hidden = self.encode(token_ids, lens, type_ids, cls_only=cls_only)
         # The reference's `type_ids.max()` (:199-202) is a host sync per batch; the checks are deferred to
         # the caller's first host read instead (ModelMemory bundles them with its result copy).
         self.last_bad_mask_flag = bad

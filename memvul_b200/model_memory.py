@@ -130,7 +130,8 @@ class ModelMemory(Model):
         ids, mask = t["token_ids"], t["mask"]
         if not ids.is_cuda:
             raise native.NativeError("memvul_b200 has no CPU path: move the model and the batch to a CUDA device")
-        hidden = self.embedder(ids, mask, t.get("type_ids"))
+        # only hidden[:, 0] is consumed (BertPooler, model_memory.py:99): let the last layer skip the other rows
+        hidden = self.embedder(ids, mask, t.get("type_ids"), cls_only=True)
         return hidden, self.embedder.last_bad_mask_flag
 
     def _instance_forward(self, sample, use_header: bool = False) -> torch.Tensor:

@@ -63,7 +63,7 @@ class ModelSingle(Model):
         if not t["token_ids"].is_cuda:
             raise native.NativeError("memvul_b200 has no CPU path: move the model and the batch to a CUDA device")
         emb = self._text_field_embedder.embedder("tokens")
-        hidden = emb(t["token_ids"], t["mask"], t.get("type_ids"))
+        hidden = emb(t["token_ids"], t["mask"], t.get("type_ids"), cls_only=True)
         B, S, H = hidden.shape
         fc = self._projector[0]._linear_layers[0]
         head = native.pool_match(hidden, S * H, B, self._bert_pooler.pooler.dense.weight,

@@ -88,7 +88,7 @@ def lib() -> ctypes.CDLL:
             L.memvul_encoder_workspace_bytes.restype = ctypes.c_size_t
             L.memvul_encoder_workspace_bytes.argtypes = [ctypes.POINTER(BertWeightsC), i32, i32]
             L.memvul_encoder_forward.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, vp, i32, i32, vp, vp,
-                                                 ctypes.c_size_t, vp]
+                                                 ctypes.c_size_t, i32, vp]
             L.memvul_mask_to_lens.argtypes = [vp, i32, i32, vp, vp, vp]
             L.memvul_bank_prepare.argtypes = [vp, vp, i32, i32, vp, vp]
             L.memvul_pool_match.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
@@ -197,10 +197,14 @@ def mask_to_lens(mask: torch.Tensor) -> torch.Tensor:
     return lens, bad
 
 
+ENC_CLS_ONLY = 1
+
+
 def encoder_forward(w: PackedBert, token_ids: torch.Tensor, lens: torch.Tensor,
                     type_ids: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """last_hidden_state fp32 [B,S,H] of HF BertModel for prefix-masked inputs."""
+                    out: Optional[torch.Tensor] = None, cls_only: bool = False) -> torch.Tensor:
+    """last_hidden_state fp32 [B,S,H] of HF BertModel for prefix-masked inputs.  ``cls_only``: only row 0 of each
+    sequence is the last layer's output (what BertPooler consumes); the last layer skips the other rows."""
     _need(token_ids, torch.int64, "token_ids")
     _need(lens, torch.int32, "lens")
     if type_ids is not None:
@@ -212,7 +216,8 @@ def encoder_forward(w: PackedBert, token_ids: torch.Tensor, lens: torch.Tensor,
     if out is None:
         out = torch.empty(B, S, w.hidden, dtype=torch.float32, device=token_ids.device)
     _check(lib().memvul_encoder_forward(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), lens.data_ptr(),
-                                        B, S, out.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()))
+                                        B, S, out.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                        ENC_CLS_ONLY if cls_only else 0, _stream()))
     return out
 
 

@@ -53,7 +53,8 @@ def test_workspace_size_formula(native_lib):
     w = native.PackedBert(synthetic_state_dict(BERT_TINY), EMB, torch.device("cpu"))
     M, H, I = 4 * 128, 128, 512
     up = lambda x: (x + 1023) // 1024 * 1024
-    assert w.workspace_bytes(4, 128) == up(M * H * 2) + up(M * 3 * H * 2) + up(M * H * 2) + up(M * I * 2)
+    tail = up(4 * H * 4) + up(4 * H * 2) + up(4 * H * 2) + up(4 * I * 2)        # [B,*] rows of the CLS-only last layer
+    assert w.workspace_bytes(4, 128) == up(M * H * 2) + up(M * 3 * H * 2) + up(M * H * 2) + up(M * I * 2) + tail
     assert w.hidden == 128 and w.layers == 2 and w.heads == 2 and w.intermediate == 512
 
 

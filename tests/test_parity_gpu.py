@@ -161,6 +161,20 @@ def test_embedder_interface_and_errors():
         assert not torch.allclose(emb(_dev(ids, mask)), h0)
 
 
+@pytest.mark.parametrize("shape_name,B,S,lens", [("tiny", 5, 200, [200, 130, 7, 64, 129]), ("base", 3, 256, [256, 100, 31])])
+def test_cls_only_last_layer_equals_full(shape_name, B, S, lens):
+    """MEMVUL_ENC_CLS_ONLY skips rows the path never reads; the [CLS] rows must equal the full forward's."""
+    from memvul_b200 import native
+    from memvul_b200.synthetic import BERT_BASE, BERT_TINY, EMB, synthetic_ids, synthetic_state_dict
+    shape = BERT_TINY if shape_name == "tiny" else BERT_BASE
+    w = native.PackedBert(synthetic_state_dict(shape), EMB, torch.device("cuda"))
+    ids, mask, _ = synthetic_ids(B, S, lens=lens, vocab_size=shape.vocab_size)
+    lens_t, _ = native.mask_to_lens(mask.cuda())
+    full = native.encoder_forward(w, ids.cuda(), lens_t)
+    cls = native.encoder_forward(w, ids.cuda(), lens_t, cls_only=True)
+    assert float((full[:, 0] - cls[:, 0]).abs().max()) < 1e-5
+
+
 def test_model_single_matches_oracle():
     from memvul_b200.custom_PTM_embedder import PretrainedTransformerEmbedder
     from memvul_b200.model_single import ModelSingle
