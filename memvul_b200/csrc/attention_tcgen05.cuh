@@ -15,31 +15,34 @@
 // Warps 0-3 : softmax (one query row per thread; S read from TMEM, P written to smem as the
 //             fp16 A operand of the second MMA, running max / sum in fp32, O rescaled in TMEM)
 // Warp 4    : lane 0 issues the TMA loads and both tcgen05.mma streams.
-// Footprint : 112 KB smem (Q 16 K, 2-stage K/V ring 64 K, P 32 K) and 256 TMEM columns (S 128, O 64) so that
-//             TWO CTAs are resident per SM: one CTA's softmax overlaps the other's MMAs/TMA.
-//             Key length <= 512 (4 blocks of 128).
+// Key blocks of 64: S = Q K_j^T is DOUBLE-buffered in TMEM (2 x 64 columns) and P in smem (2 x 16 KB), so the tensor
+// core computes S_{j+1} while the softmax warps work on S_j (the r01e capture showed them stalled 25 % of the time
+// on the S barrier with a single buffer).  Footprint: 112 KB smem (Q 16 K, 4-stage K/V ring 64 K, P 32 K) and 256
+// TMEM columns (S 2 x 64, O 64), so TWO CTAs are resident per SM.  Key length <= 512 (8 blocks of 64).
 #pragma once
 #include "ptx.cuh"
 
 namespace mv {
 
 struct AttnCfg {
-  static constexpr int BQ = 128, BKV = 128, DH = 64, MAX_KB = 4, KV_STAGES = 2;
-  static constexpr int TILE_BYTES = 128 * 64 * 2;          // 16 KB: one {64 x 128} fp16 box
-  static constexpr int P_BYTES = 2 * TILE_BYTES;           // 128 x 128 fp16 = two K-chunks
+  static constexpr int BQ = 128, BKV = 64, DH = 64, MAX_KB = 8, KV_STAGES = 4;
+  static constexpr int Q_BYTES = 128 * 64 * 2;             // 16 KB: {64 x 128} fp16 box
+  static constexpr int KV_BYTES = BKV * 64 * 2;            // 8 KB: {64 x 64} fp16 box
+  static constexpr int P_BYTES = 128 * BKV * 2;            // 16 KB: 128 x 64 fp16 = one swizzled K-chunk
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256;         // 114,944 B: two CTAs fit in 228 KB
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512;         // 115,200 B: two CTAs fit in 228 KB
   static constexpr int THREADS = 160;
   static constexpr int TMEM_COLS = 256;
   static constexpr int TM_S = 0, TM_O = 128;
 };
 
 __global__ void __launch_bounds__(AttnCfg::THREADS, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int* __restrict__ lens,
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
+                         const int* __restrict__ lens,
                          __half* __restrict__ ctx, int S, int H) {
   using C = AttnCfg;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -61,19 +64,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
 
   extern __shared__ __align__(1024) uint8_t smem[];        // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* q_full = bars;                 // [1]
-  uint64_t* k_full = bars + 1;             // [4]
-  uint64_t* v_full = bars + 5;             // [4]
-  uint64_t* s_full = bars + 9;             // [4]  QK^T of block j complete
-  uint64_t* p_full = bars + 13;            // [4]  P_j in smem, S_j drained, O rescaled   (4 warp arrivals)
-  uint64_t* pv_done = bars + 17;           // [4]  P_j V_j accumulated into O
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* q_full = bars;                           // [1]
+  uint64_t* k_full = bars + 1;                       // [8]
+  uint64_t* v_full = k_full + C::MAX_KB;             // [8]
+  uint64_t* s_full = v_full + C::MAX_KB;             // [8]  QK^T of block j complete
+  uint64_t* p_full = s_full + C::MAX_KB;             // [8]  P_j in smem, S_j drained, O rescaled   (4 warp arrivals)
+  uint64_t* pv_done = p_full + C::MAX_KB;            // [8]  P_j V_j accumulated into O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + C::MAX_KB);
 
-  const int nkb = (len + C::BKV - 1) / C::BKV;     // 1..4 key blocks; every barrier is used once (parity 0)
+  const int nkb = (len + C::BKV - 1) / C::BKV;     // 1..8 key blocks; every barrier is used once (parity 0)
 
   if (warp_idx == 4) {
     if (lane == 0) {
       prefetch_tmap(&tmap_qkv);
+      prefetch_tmap(&tmap_kv);
       mbar_init(q_full, 1);
       for (int j = 0; j < C::MAX_KB; ++j) {
         mbar_init(&k_full[j], 1);
@@ -100,21 +104,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
       auto load_kv = [&](int j) {
         const int st = j % C::KV_STAGES;
         const int row_k = static_cast<int>(row_base) + j * C::BKV;
-        mbar_arrive_expect_tx(&k_full[j], C::TILE_BYTES);
-        tma_load_2d(smem + C::OFF_K + st * C::TILE_BYTES, &tmap_qkv, &k_full[j], H + h * C::DH, row_k, kEvictLast);
-        mbar_arrive_expect_tx(&v_full[j], C::TILE_BYTES);
-        tma_load_2d(smem + C::OFF_V + st * C::TILE_BYTES, &tmap_qkv, &v_full[j], 2 * H + h * C::DH, row_k, kEvictLast);
+        mbar_arrive_expect_tx(&k_full[j], C::KV_BYTES);
+        tma_load_2d(smem + C::OFF_K + st * C::KV_BYTES, &tmap_kv, &k_full[j], H + h * C::DH, row_k, kEvictLast);
+        mbar_arrive_expect_tx(&v_full[j], C::KV_BYTES);
+        tma_load_2d(smem + C::OFF_V + st * C::KV_BYTES, &tmap_kv, &v_full[j], 2 * H + h * C::DH, row_k, kEvictLast);
       };
-      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
       tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_q, kEvictFirst);
       for (int j = 0; j < nkb && j < C::KV_STAGES; ++j) load_kv(j);
       // ---------------- MMA issue ----------------
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, false, false);   // S = Q K^T   (both K-major)
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);     // O += P V    (V is N-major)
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, C::BKV, false, false);   // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);        // O += P V    (V is N-major)
       const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + C::OFF_Q));
       auto issue_qk = [&](int j) {
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + (j % C::KV_STAGES) * C::TILE_BYTES));
-        const uint32_t d = tmem_base + C::TM_S;
+        mbar_wait(&k_full[j], 0);
+        tc_fence_after();
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + (j % C::KV_STAGES) * C::KV_BYTES));
+        const uint32_t d = tmem_base + C::TM_S + static_cast<uint32_t>((j & 1) * C::BKV);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
@@ -122,30 +128,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
         umma_commit(&s_full[j]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
       issue_qk(0);
+      if (nkb > 1) issue_qk(1);
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&p_full[j], 0);          // P_j in smem, S drained (single S buffer), O rescaled
-        if (j + 1 < nkb) {
-          mbar_wait(&k_full[j + 1], 0);
-          tc_fence_after();
-          issue_qk(j + 1);                 // overlaps the softmax of block j+1 with P_j V_j below
-        }
+        mbar_wait(&p_full[j], 0);          // P_j in smem, S[j&1] drained, O rescaled
         mbar_wait(&v_full[j], 0);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + C::OFF_P);
-        const uint32_t v_addr = smem_u32(smem + C::OFF_V + (j % C::KV_STAGES) * C::TILE_BYTES);
+        const uint32_t p_addr = smem_u32(smem + C::OFF_P + (j & 1) * C::P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + C::OFF_V + (j % C::KV_STAGES) * C::KV_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // A = P: K-major, two 64-wide K chunks of 16 KB, 32 B per K=16 step inside a chunk.
-          const uint64_t a_desc = umma_desc_sw128(p_addr + (kk >> 2) * C::TILE_BYTES) +
-                                  static_cast<uint64_t>((kk & 3) * 2);
-          // B = V: N-major (64 dh contiguous = one swizzle row per key); 16 keys = 2048 B per step.
+        for (int kk = 0; kk < C::BKV / 16; ++kk) {
+          // A = P: K-major 64-wide chunk, 32 B per K=16 step.  B = V: N-major (one 128 B swizzle row per key),
+          // 16 keys = 2048 B per step.
+          const uint64_t a_desc = umma_desc_sw128(p_addr) + static_cast<uint64_t>(kk * 2);
           const uint64_t b_desc = umma_desc_sw128(v_addr + kk * 2048);
           umma_f16_ss(tmem_base + C::TM_O, a_desc, b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[j]);
+        if (j + 2 < nkb) issue_qk(j + 2);  // S[j&1] is free (p_full[j]); runs under the softmax of block j+1
         if (j + C::KV_STAGES < nkb) {      // recycle this K/V stage once Q K_j^T and P_j V_j have retired
           mbar_wait(&pv_done[j], 0);
           load_kv(j + C::KV_STAGES);
@@ -161,51 +161,60 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const int
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(&s_full[j], 0);
       tc_fence_after();
-      uint32_t s[4][32];
-      const uint32_t s_addr = tmem_base + lane_addr + C::TM_S;
+      uint32_t s[2][32];
+      const uint32_t s_addr = tmem_base + lane_addr + C::TM_S + static_cast<uint32_t>((j & 1) * C::BKV);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_addr + cc * 32, s[cc]);
+      for (int cc = 0; cc < 2; ++cc) tmem_ld_32x32b_x32(s_addr + cc * 32, s[cc]);
       tmem_wait_ld();
       const int valid = min(C::BKV, len - j * C::BKV);         // >= 1
-      float mx = -INFINITY;
+      if (valid < C::BKV) {                                    // only the last key block of a sequence is ragged
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
+        for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (cc * 32 + i < valid) ? __uint_as_float(s[cc][i]) : -INFINITY;
-          s[cc][i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i >= valid) s[cc][i] = 0xff800000u;   // -inf: exp2 -> 0, never the max
+      }
+      // row max: 4 independent chains of 3-input max (one chain of dependent FMNMX would be latency-bound)
+      float mx4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t* sp = &s[q >> 1][(q & 1) * 16];
+        float m = __uint_as_float(sp[0]);
+#pragma unroll
+        for (int i = 1; i < 15; i += 2) m = max3(m, __uint_as_float(sp[i]), __uint_as_float(sp[i + 1]));
+        mx4[q] = fmaxf(m, __uint_as_float(sp[15]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float mc = m_new * c;
-      float l_blk = 0.f;
-      if (j > 0) {
-        mbar_wait(&pv_done[j - 1], 0);       // O holds blocks 0..j-1 and the single P buffer is free again
-        tc_fence_after();
-      }
-      uint8_t* p_row = smem + C::OFF_P + r * 128;
+      uint8_t* p_row = smem + C::OFF_P + (j & 1) * C::P_BYTES + r * 128;     // P[j&1]: PV_{j-2} retired long ago
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};    // independent partial sums (ILP)
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {              // 8 columns -> one 16 B unit of the swizzled row
           float e[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            e[t] = exp2f(fmaf(__uint_as_float(s[cc][u * 8 + t]), c, -mc));    // exp2(-inf) = 0 for masked keys
-            l_blk += e[t];
-          }
+          for (int t = 0; t < 8; ++t)
+            e[t] = ex2_approx(fmaf(__uint_as_float(s[cc][u * 8 + t]), c, -mc));    // ex2(-inf) = 0 for masked keys
+          l4[0] += e[0] + e[1];
+          l4[1] += e[2] + e[3];
+          l4[2] += e[4] + e[5];
+          l4[3] += e[6] + e[7];
           uint4 pk;
           pk.x = pack_half2(e[0], e[1]);
           pk.y = pack_half2(e[2], e[3]);
           pk.z = pack_half2(e[4], e[5]);
           pk.w = pack_half2(e[6], e[7]);
-          const int unit = (cc & 1) * 4 + u;       // 16 B unit inside the 64-column chunk
-          const int chunk = cc >> 1;
-          *reinterpret_cast<uint4*>(p_row + chunk * C::TILE_BYTES + ((unit ^ (r & 7)) << 4)) = pk;
+          const int unit = cc * 4 + u;             // 16 B unit inside the 64-column row
+          *reinterpret_cast<uint4*>(p_row + ((unit ^ (r & 7)) << 4)) = pk;
         }
       }
-      const float alpha = exp2f((m_run - m_new) * c);          // 0 on the first block (m_run = -inf)
+      const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      const float alpha = ex2_approx((m_run - m_new) * c);     // 0 on the first block (m_run = -inf)
       if (j > 0) {
+        mbar_wait(&pv_done[j - 1], 0);                         // O holds blocks 0..j-1
+        tc_fence_after();
         if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {

@@ -286,8 +286,9 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  CUtensorMap tq;
+  CUtensorMap tq, tkv;
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, &tq)) return rc;
+  if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, mv::AttnCfg::BKV, &tkv)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(mv::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -297,7 +298,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   dim3 grid(first_tile_only ? 1 : (S + 127) / 128, H / 64, B);
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, lens, reinterpret_cast<__half*>(ctx), S, H);
+      tq, tkv, lens, reinterpret_cast<__half*>(ctx), S, H);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }

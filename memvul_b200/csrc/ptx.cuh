@@ -256,6 +256,11 @@ __device__ __forceinline__ float erf_as(float x) {
   const float y = fmaf(-p * t, e, 1.0f);
   return copysignf(y, x);
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {      // sm_100 three-input max: one FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
