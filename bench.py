@@ -33,7 +33,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_PER_GPU, SEQ, ANCHORS, SEED = 64, 512, 129, 2021
+B_PER_GPU, SEQ, ANCHORS, SEED = int(os.environ.get("MEMVUL_BENCH_B", "64")), 512, 129, 2021   # env override: experiments only
 METRIC, UNIT = "issue-reports/sec, bert-base seq512 + CWE memory", "issues/s"
 
 

@@ -185,7 +185,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         mx4[q] = fmaxf(m, __uint_as_float(sp[15]));
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m_run, mx);
+      // Lazy rescaling: keep exponentiating against the stale reference m_run until some row's maximum has grown by
+      // more than 2^8 relative to it (P <= 256 stays far inside fp16, O / l accumulate in fp32 and the common factor
+      // cancels in O / l).  With a fresh maximum in almost every block, rescaling O in TMEM every time cost as many
+      // FMULs as the exponentials themselves plus a TMEM load/store round trip on the critical path.
+      const bool grow = (mx - m_run) * c > 8.0f;               // true on the first block (m_run = -inf)
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      const float m_new = grow ? mx : m_run;
       const float mc = m_new * c;
       uint8_t* p_row = smem + C::OFF_P + (j & 1) * C::P_BYTES + r * 128;     // P[j&1]: PV_{j-2} retired long ago
       float l4[4] = {0.f, 0.f, 0.f, 0.f};    // independent partial sums (ILP)
@@ -215,7 +221,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       if (j > 0) {
         mbar_wait(&pv_done[j - 1], 0);                         // O holds blocks 0..j-1
         tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new > m_run)) {
+        if (any_grow) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t o[32];

@@ -41,43 +41,57 @@ struct PoolMatchParams {
   int B, G, H, D, same_idx, b_chunk, phase_mask;
 };
 
-// out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]); one output column per warp, W row held in registers.
+// out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]).  Work item = (output column n, chunk of 8 rows b): the W row lives in
+// registers, the 8 dot products are independent chains (ILP) and their warp reductions interleave; with N * ceil(B/8)
+// items the phase spreads over every resident warp instead of serialising B rows per column.
 template <int ACT /*0 tanh, 1 relu*/>
 __device__ __forceinline__ void dense_rows_phase(const float* x, long long x_stride, const float* __restrict__ W,
                                                  const float* __restrict__ bias, float* out, int B, int N, int K,
                                                  int gwarp, int nwarps, int lane) {
   constexpr int MAXV = 6;                       // K <= 768
+  constexpr int BCH = 8;
   const int nv = K >> 7;                        // float4 per lane (K multiple of 128)
-  for (int n = gwarp; n < N; n += nwarps) {
+  const int nbc = (B + BCH - 1) / BCH;
+  const int items = N * nbc;
+  for (int item = gwarp; item < items; item += nwarps) {
+    const int n = item / nbc, b0 = (item - n * nbc) * BCH;
     float4 w[MAXV];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       w[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + i * 128 + lane * 4))
                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float bn = bias[n];
-    for (int b = 0; b < B; ++b) {
-      const float* xr = x + static_cast<size_t>(b) * x_stride;
-      float acc = 0.f;
+    float acc[BCH];
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        if (i < nv) {
-          const float4 xv = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-          acc = fmaf(xv.x, w[i].x, acc);
-          acc = fmaf(xv.y, w[i].y, acc);
-          acc = fmaf(xv.z, w[i].z, acc);
-          acc = fmaf(xv.w, w[i].w, acc);
+    for (int r = 0; r < BCH; ++r) acc[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < nv) {
+#pragma unroll
+        for (int r = 0; r < BCH; ++r) {
+          const int b = min(b0 + r, B - 1);     // tail rows recompute the last row; never stored
+          const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * x_stride + i * 128 + lane * 4);
+          acc[r] = fmaf(xv.x, w[i].x, acc[r]);
+          acc[r] = fmaf(xv.y, w[i].y, acc[r]);
+          acc[r] = fmaf(xv.z, w[i].z, acc[r]);
+          acc[r] = fmaf(xv.w, w[i].w, acc[r]);
         }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const float v = acc + bn;
-        out[static_cast<size_t>(b) * N + n] = ACT == 0 ? tanhf(v) : fmaxf(v, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < BCH; ++r) acc[r] = warp_sum(acc[r]);
+    const float bn = bias[n];
+#pragma unroll
+    for (int r = 0; r < BCH; ++r) {
+      if (lane == r && b0 + r < B) {
+        const float v = acc[r] + bn;
+        out[static_cast<size_t>(b0 + r) * N + n] = ACT == 0 ? tanhf(v) : fmaxf(v, 0.f);
       }
     }
   }
 }
 
-__device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp, int nwarps, int lane) {
+__device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp, int nwarps, int lane,
+                                            unsigned long long* sbest) {
   constexpr int MAXJ = 4;                       // D <= 512
   const int D = p.D, G = p.G, B = p.B;
   const int nd4 = D >> 2;
@@ -95,20 +109,24 @@ __device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp,
     w0[j] = ok ? __ldg(reinterpret_cast<const float4*>(wd0) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
     w1[j] = ok ? __ldg(reinterpret_cast<const float4*>(wd1) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int item = gwarp; item < items; item += nwarps) {
-    const int gq = item / n_bc, bc = item - gq * n_bc;
-    const int g0 = gq * 4;
-    float4 v[4][MAXJ];
+  auto load_quad = [&](int item, float4 (&dst)[4][MAXJ]) {
+    const int g0n = (item / n_bc) * 4;
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
-      const int g = min(g0 + gi, G - 1);        // clamp: tail anchors recompute the last row, never stored
+      const int g = min(g0n + gi, G - 1);       // clamp: tail anchors recompute the last row, never stored
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) {
         const int k4 = lane + 32 * j;
-        v[gi][j] = (k4 < nd4) ? __ldg(reinterpret_cast<const float4*>(p.bank + static_cast<size_t>(g) * D) + k4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[gi][j] = (k4 < nd4) ? __ldg(reinterpret_cast<const float4*>(p.bank + static_cast<size_t>(g) * D) + k4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  };
+  float4 v[4][MAXJ];
+  for (int item = gwarp; item < items; item += nwarps) {
+    const int gq = item / n_bc, bc = item - gq * n_bc;
+    const int g0 = gq * 4;
+    load_quad(item, v);
     const int b_end = min(B, (bc + 1) * p.b_chunk);
     for (int b = bc * p.b_chunk; b < b_end; ++b) {
       float acc[8];
@@ -185,11 +203,17 @@ __device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp,
       // max over the 4 anchors of this warp (keys are 0 in the other lanes), one atomic per (b, quad)
       key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
       key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
-      if (lane == 0) atomicMax(p.best_key + b, key);
+      // block-level arg-max first (shared-memory atomics), one global atomic per (block, query) afterwards: with one
+      // global atomicMax per (query, anchor quad) the B target addresses serialised B*G/4 L2 atomics.
+      if (lane == 0) {
+        if (sbest) atomicMax(sbest + b, key);
+        else atomicMax(p.best_key + b, key);
+      }
     }
   }
 }
 
+constexpr int kMaxSmemBest = 1024;     // queries per launch whose running arg-max lives in shared memory (8 KB)
 enum : int { PM_POOL = 1, PM_HEADER = 2, PM_UTERM = 4, PM_MATCH = 8, PM_FINAL = 16, PM_ALL = 31 };
 
 __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p) {
@@ -230,7 +254,18 @@ __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p
   }
   if (p.phase_mask & PM_MATCH) {
     phase_sync();
-    match_phase(p, gwarp, nwarps, lane);
+    __shared__ unsigned long long sbest_buf[kMaxSmemBest];
+    unsigned long long* sbest = p.B <= kMaxSmemBest ? sbest_buf : nullptr;
+    if (sbest) {
+      for (int b = threadIdx.x; b < p.B; b += blockDim.x) sbest[b] = 0ull;
+      __syncthreads();
+    }
+    match_phase(p, gwarp, nwarps, lane, sbest);
+    if (sbest) {
+      __syncthreads();
+      for (int b = threadIdx.x; b < p.B; b += blockDim.x)
+        if (sbest[b]) atomicMax(p.best_key + b, sbest[b]);
+    }
   }
   if (p.phase_mask & PM_FINAL) {
     phase_sync();

@@ -55,5 +55,10 @@ def run_case(B, G, iters=20, phase=None):
 if __name__ == "__main__":
     cases = [(4, 65536), (8, 65536), (2, 262144), (256, 16384), (64, 129)]
     for B, G in cases:
-        print(json.dumps(run_case(B, G)), flush=True)
-        print(json.dumps(run_case(B, G, phase=N.PM_UTERM | N.PM_MATCH | N.PM_FINAL)), flush=True)
+        for ph in (None, N.PM_UTERM | N.PM_MATCH | N.PM_FINAL):
+            d = run_case(B, G, phase=ph)
+            if "--table" in sys.argv:
+                print(f"B={d['B']:4d} G={d['G']:7d} {d['phases']:12s} {d['us']:9.1f} us {d['hbm_GBps']:8.1f} GB/s "
+                      f"{d['fp32_lane_Tinstr_per_s']:.2f} Tlane-instr/s", flush=True)
+            else:
+                print(json.dumps(d), flush=True)
