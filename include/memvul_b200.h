@@ -115,6 +115,10 @@ int memvul_single_head(const float* feat, const float* w_cls, int B, int D, floa
 /* out = epilogue(A[M,K] fp16 x W[N,K]^T fp16); K % 64 == 0, N % 128 == 0; resid/out leading dim = N. */
 int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
                     int K, int epilogue, void* stream);
+/* x32 (fp32) and x16 (fp16) = LayerNorm(A[M,K] W[768,K]^T + bias + resid) in one kernel (six-CTA clusters exchange the
+ * row statistics through distributed shared memory); N must be 768, M >= 256.  In place (x32 == resid) is allowed. */
+int memvul_gemm_ln_f16(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
+                       const float* beta, float eps, float* x32, void* x16, int M, int N, int K, void* stream);
 /* ctx[B*S,H] fp16 = softmax(QK^T/8 + mask)V per head from qkv [B*S,3H] fp16; head_dim 64, S <= 512. */
 int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream);
 /* x32/x16 = LayerNorm(y) rows; x32 or x16 may be NULL; in-place x32 == y allowed. */

@@ -1,0 +1,281 @@
+// Fused  x = LayerNorm(A W^T + bias + resid)  for the two residual GEMMs of a BERT layer (attention output
+// projection, FFN down-projection; SURVEY.md 2.2 rows K4 and K6 in full), N = 768.
+//
+// A LayerNorm row needs all 768 outputs, but one CTA pair's TMEM holds only a 256-column accumulator (twice).  So a
+// CLUSTER OF SIX CTAs = three cta_group::2 pairs works on one 256-row block: pair p owns columns [256p, 256p+256),
+// each CTA 128 of the rows.  Per tile, in every CTA's epilogue warps:
+//   pass 1  v = acc + bias + resid (residual 32x32 boxes arrive by TMA, 2 in flight); row sums of v and v^2;
+//           v is written BACK INTO TMEM (tcgen05.st) -- the accumulator stage doubles as the stash for pass 2;
+//   exchange each thread publishes its (sum, sumsq) for (row, column half) into the shared memory of the three CTAs
+//           that own the same rows (st.shared::cluster), then a release/acquire mbarrier round at cluster scope;
+//   pass 2  mean / rstd from the 6 partials; y = (v - mean) * rstd * gamma + beta is staged in swizzled smem and
+//           leaves by TMA store twice: fp32 (the residual stream) and fp16 (the next GEMM's A operand).
+// This removes the stand-alone LayerNorm kernels (9-13 % of the step in r01c/r01d) and the fp32 round trip of the
+// pre-LN sum through HBM: 10 bytes per element instead of 18.
+// Main loop, barriers and roles are those of gemm_tcgen05_2cta.cuh (warp 0 TMA, warp 1 MMA issue on even ranks,
+// warp 2 TMEM alloc, warps 4-11 epilogue).
+#pragma once
+#include "gemm_tcgen05_2cta.cuh"
+
+namespace mv {
+
+struct GemmLnCfg {
+  static constexpr int N = 768, PAIRS = 3, CLUSTER = 6;
+  static constexpr int BM = 256, BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64;
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = BM_CTA * BK * 2, B_BYTES = BN_CTA * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int THREADS = 384, EPI_WARPS = 8;
+  static constexpr int STG_BYTES = 4096;                                   // 32 rows x 128 B, SWIZZLE_128B
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;                     // [8 warps][2] staging buffers
+  static constexpr int OFF_PRM = OFF_STG + EPI_WARPS * 2 * STG_BYTES;      // [8 warps][bias|gamma|beta][128] floats
+  static constexpr int OFF_STATS = OFF_PRM + EPI_WARPS * 3 * 128 * 4;      // [2 slots][6 sources][128 rows] float2
+  static constexpr int OFF_BAR = OFF_STATS + 2 * 6 * 128 * 8;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared-memory limit");
+};
+
+__global__ void __cluster_dims__(6, 1, 1) __launch_bounds__(384, 1)
+gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                           const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x32,
+                           const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  using Cfg = GemmLnCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;                      // [EPI_WARPS][2]
+  uint64_t* stats_bar = res_bar + 2 * Cfg::EPI_WARPS;      // [2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stats_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = static_cast<int>(threadIdx.x & 31);
+  const uint32_t cta_rank = cluster_ctarank();             // 0..5
+  const uint32_t pair = cta_rank >> 1;                     // column block n_blk
+  const uint32_t half_m = cta_rank & 1u;                   // which 128 rows of the 256-row tile
+  const uint32_t leader_rank = cta_rank & ~1u;
+  const bool leader = half_m == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_res); prefetch_tmap(&tmap_x32); prefetch_tmap(&tmap_x16);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], Cfg::PAIRS * Cfg::EPI_WARPS);     // 3 CTAs x 8 warps
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = (M + Cfg::BM - 1) / Cfg::BM;       // 256-row blocks; every cluster covers all 768 columns
+  const int num_kb = K / Cfg::BK;
+  const int cluster_id = blockIdx.x / Cfg::CLUSTER;
+  const int num_clusters = gridDim.x / Cfg::CLUSTER;
+  const int row_b = static_cast<int>(pair) * Cfg::BN + static_cast<int>(half_m) * Cfg::BN_CTA;   // this CTA's W rows
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (all CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int row_a = tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
+          tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (even rank of each pair) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, Cfg::BN, false, false);
+      const uint16_t pair_mask = static_cast<uint16_t>(0b11u << (pair * 2));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(sa);
+          const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k)
+            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], pair_mask);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tfull_bar[acc], pair_mask);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue: bias + residual + LayerNorm =====================
+    const int ew = warp_idx - 4;
+    const int quarter = ew & 3;
+    const int half_sel = ew >> 2;
+    constexpr int NCHUNK = 4;                              // 4 x 32 columns per warp
+    float* prm = reinterpret_cast<float*>(smem + Cfg::OFF_PRM) + ew * 3 * 128;
+    uint8_t* buf0 = smem + Cfg::OFF_STG + ew * 2 * Cfg::STG_BYTES;       // residual ping / fp32 output staging
+    uint8_t* buf1 = buf0 + Cfg::STG_BYTES;                               // residual pong / fp16 output staging
+    uint64_t* my_res_bar = res_bar + 2 * ew;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const int col0 = static_cast<int>(pair) * Cfg::BN + half_sel * 128;  // first of this warp's 128 columns
+    const int row_in_cta = quarter * 32 + lane;
+    const uint32_t stats_base = smem_u32(smem + Cfg::OFF_STATS);
+    const uint32_t my_src = pair * 2 + static_cast<uint32_t>(half_sel);  // 0..5: which (pair, column half) I publish
+    // parameters of my 128 columns, once (the CTA's column block never changes)
+    reinterpret_cast<float4*>(prm)[lane] = __ldg(reinterpret_cast<const float4*>(bias + col0) + lane);
+    reinterpret_cast<float4*>(prm + 128)[lane] = __ldg(reinterpret_cast<const float4*>(gamma + col0) + lane);
+    reinterpret_cast<float4*>(prm + 256)[lane] = __ldg(reinterpret_cast<const float4*>(beta + col0) + lane);
+    __syncwarp();
+
+    auto strip_row0 = [&](int tile) { return tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA + quarter * 32; };
+    auto issue_res = [&](int tile, int c) {                 // residual box (rows of `tile`, chunk c) -> buffer c & 1
+      uint8_t* dst = (c & 1) ? buf1 : buf0;
+      mbar_arrive_expect_tx(&my_res_bar[c & 1], Cfg::STG_BYTES);
+      tma_load_2d(dst, &tmap_res, &my_res_bar[c & 1], col0 + c * 32, strip_row0(tile), kEvictFirst);
+    };
+    if (lane == 0 && cluster_id < num_tiles) { issue_res(cluster_id, 0); issue_res(cluster_id, 1); }
+
+    int acc = 0;
+    uint32_t acc_phase = 0, gc = 0, it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int row0 = strip_row0(tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                              static_cast<uint32_t>(acc * Cfg::BN + half_sel * 128);
+      // ---------------- pass 1: v = acc + bias + resid -> TMEM, row statistics ----------------
+      float s1 = 0.f, s2 = 0.f;
+      uint32_t r[2][32];
+      tmem_ld_32x32b_x32(t_addr, r[0]);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+        const uint32_t(&a)[32] = r[c & 1];
+        uint8_t* rowp = ((c & 1) ? buf1 : buf0) + lane * 128;
+        mbar_wait(&my_res_bar[c & 1], (gc >> 1) & 1u);
+        ++gc;
+        uint32_t v[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(rowp + ((static_cast<uint32_t>(u) ^ sw) << 4));
+          const float4 bb = *reinterpret_cast<const float4*>(prm + c * 32 + 4 * u);
+          const float v0 = __uint_as_float(a[4 * u + 0]) + bb.x + x.x;
+          const float v1 = __uint_as_float(a[4 * u + 1]) + bb.y + x.y;
+          const float v2 = __uint_as_float(a[4 * u + 2]) + bb.z + x.z;
+          const float v3 = __uint_as_float(a[4 * u + 3]) + bb.w + x.w;
+          s1 += (v0 + v1) + (v2 + v3);
+          s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
+          v[4 * u + 0] = __float_as_uint(v0); v[4 * u + 1] = __float_as_uint(v1);
+          v[4 * u + 2] = __float_as_uint(v2); v[4 * u + 3] = __float_as_uint(v3);
+        }
+        tmem_st_32x32b_x32(t_addr + c * 32, v);            // stash for pass 2
+        __syncwarp();                                      // every lane has read this residual buffer
+        if (lane == 0 && c + 2 < NCHUNK) issue_res(tile, c + 2);
+      }
+      // ---------------- exchange the row statistics with the two other column blocks ----------------
+      const uint32_t slot = it & 1u;
+      {
+        const uint32_t off = ((slot * 6u + my_src) * 128u + static_cast<uint32_t>(row_in_cta)) * 8u;
+#pragma unroll
+        for (uint32_t pp = 0; pp < 3; ++pp) st_cluster_f32x2(mapa_u32(stats_base + off, pp * 2 + half_m), s1, s2);
+        fence_acq_rel_cluster();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (uint32_t pp = 0; pp < 3; ++pp) mbar_arrive_release_cluster(&stats_bar[slot], pp * 2 + half_m);
+        }
+      }
+      tmem_wait_st();
+      mbar_wait_cluster(&stats_bar[slot], (it >> 1) & 1u);
+      float S1 = 0.f, S2 = 0.f;
+      {
+        const float2* st = reinterpret_cast<const float2*>(smem + Cfg::OFF_STATS) + (slot * 6) * 128 + row_in_cta;
+#pragma unroll
+        for (int src = 0; src < 6; ++src) { const float2 p2 = st[src * 128]; S1 += p2.x; S2 += p2.y; }
+      }
+      const float mean = S1 * (1.0f / Cfg::N);
+      const float var = fmaxf(S2 * (1.0f / Cfg::N) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + eps);
+      // ---------------- pass 2: normalise, stage, TMA-store fp32 + fp16 ----------------
+      tmem_ld_32x32b_x32(t_addr, r[0]);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+        const uint32_t(&a)[32] = r[c & 1];
+        if (lane == 0 && c > 0) bulk_wait_read_all();      // previous boxes have left buf0 (and buf1 when c is even)
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 g = *reinterpret_cast<const float4*>(prm + 128 + c * 32 + 4 * u);
+          const float4 be = *reinterpret_cast<const float4*>(prm + 256 + c * 32 + 4 * u);
+          float4 o;
+          o.x = (__uint_as_float(a[4 * u + 0]) - mean) * rstd * g.x + be.x;
+          o.y = (__uint_as_float(a[4 * u + 1]) - mean) * rstd * g.y + be.y;
+          o.z = (__uint_as_float(a[4 * u + 2]) - mean) * rstd * g.z + be.z;
+          o.w = (__uint_as_float(a[4 * u + 3]) - mean) * rstd * g.w + be.w;
+          *reinterpret_cast<float4*>(buf0 + lane * 128 + ((static_cast<uint32_t>(u) ^ sw) << 4)) = o;
+          // fp16 copy: 4 values = 8 B; two of them fill one 16 B unit of the 32 x 64 box (chunk parity = 64 B half)
+          const uint32_t h_unit = static_cast<uint32_t>((c & 1) * 4 + (u >> 1));
+          uint2 hv;
+          hv.x = pack_half2(o.x, o.y);
+          hv.y = pack_half2(o.z, o.w);
+          *reinterpret_cast<uint2*>(buf1 + lane * 128 + ((h_unit ^ sw) << 4) + (u & 1) * 8) = hv;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_x32, buf0, col0 + c * 32, row0);
+          if (c & 1) tma_store_2d(&tmap_x16, buf1, col0 + (c >> 1) * 64, row0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(&tempty_bar[acc], leader_rank);          // accumulator stage is free again
+        bulk_wait_read_all();                                        // staging buffers are free again
+        const int nt = tile + num_clusters;
+        if (nt < num_tiles) { issue_res(nt, 0); issue_res(nt, 1); }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace mv

@@ -16,6 +16,7 @@
 #include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
+#include "gemm_ln_tcgen05.cuh"
 #include "pool_match.cuh"
 #include "rowwise.cuh"
 
@@ -280,6 +281,47 @@ int gemm_impl(const void* a, const void* w, const float* bias, const float* resi
                : launch_gemm_epi<128>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st);
 }
 
+
+// Fused residual GEMM + LayerNorm (N == 768): x32/x16 = LN(A W^T + bias + resid).  Falls back to the caller's
+// two-kernel path (returns 1) when the shape does not qualify.
+int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
+                 const float* beta, float eps, float* x32, void* x16, int M, int N, int K, cudaStream_t st) {
+  using Cfg = mv::GemmLnCfg;
+  static const bool disabled = [] { const char* e = getenv("MEMVUL_FUSED_LN"); return e && strcmp(e, "0") == 0; }();
+  if (disabled || N != Cfg::N || K % 64 != 0 || M < Cfg::BM) return 1;
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  auto kern = mv::gemm_ln_f16_tcgen05_kernel;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Cfg::CLUSTER * (di.sms / Cfg::CLUSTER));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Cfg::CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) return fail(MEMVUL_E_CUDA, "fused GEMM+LayerNorm: no 6-CTA cluster fits on this device");
+    max_clusters = n;
+  }
+  CUtensorMap ta, tb, tres, t32, t16;
+  if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
+  if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, &tb)) return rc;
+  if (int rc = make_map(resid, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tres)) return rc;
+  if (int rc = make_map(x32, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &t32)) return rc;
+  if (int rc = make_map(x16, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2, &t16)) return rc;
+  const int tiles = (M + Cfg::BM - 1) / Cfg::BM;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  LaunchScope ls(g_cls, st);
+  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tres, t32, t16, M, K, bias, gamma, beta, eps);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
 int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st,
                    bool first_tile_only = false) {
   if (B <= 0 || S <= 0 || S > 512) return fail(MEMVUL_E_INVALID, "attention needs 1 <= S <= 512 (B=%d S=%d)", B, S);
@@ -406,6 +448,15 @@ int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float
   return gemm_impl(a, w, bias, resid, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
 }
 
+
+int memvul_gemm_ln_f16(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
+                       const float* beta, float eps, float* x32, void* x16, int M, int N, int K, void* stream) {
+  if (!a || !w || !bias || !resid || !gamma || !beta || !x32 || !x16) return fail(MEMVUL_E_INVALID, "gemm_ln null pointer");
+  int rc = gemm_ln_impl(a, w, bias, resid, gamma, beta, eps, x32, x16, M, N, K, static_cast<cudaStream_t>(stream));
+  if (rc == 1) return fail(MEMVUL_E_INVALID, "gemm_ln needs N == 768, K %% 64 == 0, M >= 256 (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+
 int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream) {
   if (!qkv || !lens || !ctx) return fail(MEMVUL_E_INVALID, "attention null pointer");
   return attention_impl(qkv, lens, ctx, B, S, H, static_cast<cudaStream_t>(stream));
@@ -473,13 +524,21 @@ int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_id
     if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
     if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st)) return rc;
     { ClassScope cs(KC_GEMM_ATTN_OUT);
-    if (int rc = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
-    if (int rc = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
+      int rc = gemm_ln_impl(ws.ctx, L.w_ao, L.b_ao, x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, H, st);
+      if (rc < 0) return rc;
+      if (rc == 1) {      // shape not covered by the fused kernel: GEMM + stand-alone LayerNorm
+        if (int rc2 = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc2;
+        if (int rc2 = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc2;
+      } }
     { ClassScope cs(KC_GEMM_FFN_UP);
     if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc; }
     { ClassScope cs(KC_GEMM_FFN_DOWN);
-    if (int rc = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
-    if (int rc = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc;
+      int rc = gemm_ln_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, I, st);
+      if (rc < 0) return rc;
+      if (rc == 1) {
+        if (int rc2 = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc2;
+        if (int rc2 = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc2;
+      } }
   }
   return MEMVUL_OK;
 }

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmemvul_b200.so")
-SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "attention_tcgen05.cuh", "rowwise.cuh", "pool_match.cuh"]
+SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh", "rowwise.cuh", "pool_match.cuh"]
 
 EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32 = 0, 1, 2
 PM_POOL, PM_HEADER, PM_UTERM, PM_MATCH, PM_FINAL, PM_ALL = 1, 2, 4, 8, 16, 31
@@ -68,7 +68,7 @@ class BertWeightsC(ctypes.Structure):
 
 EXPORTS = ["memvul_abi_version", "memvul_last_error", "memvul_encoder_workspace_bytes", "memvul_encoder_forward",
            "memvul_mask_to_lens", "memvul_bank_prepare", "memvul_pool_match", "memvul_single_head",
-           "memvul_gemm_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm",
+           "memvul_gemm_f16", "memvul_gemm_ln_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm",
            "memvul_launch_count", "memvul_profile_enable", "memvul_profile_read"]
 KERNEL_CLASSES = ["embed_ln", "gemm_qkv", "attention", "gemm_attn_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down",
                   "pool_match", "other"]
@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
                                             vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
             L.memvul_single_head.argtypes = [vp, vp, i32, i32, vp, vp, vp]
             L.memvul_gemm_f16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+            L.memvul_gemm_ln_f16.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]
             L.memvul_attention_f16.argtypes = [vp, vp, vp, i32, i32, i32, vp]
             L.memvul_layernorm.argtypes = [vp, vp, vp, f32, vp, vp, i32, i32, vp]
             L.memvul_embed_layernorm.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, i32, i32, vp, vp, vp]
@@ -285,6 +286,21 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int
     _check(lib().memvul_gemm_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid), out.data_ptr(), M, N, K,
                                  epilogue, _stream()))
     return out
+
+
+def gemm_ln_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: torch.Tensor, gamma: torch.Tensor,
+                beta: torch.Tensor, eps: float = 1e-12, inplace: bool = False):
+    """Fused LayerNorm(a @ w.T + bias + resid) -> (fp32, fp16); N must be 768."""
+    _need(a, torch.float16, "a")
+    _need(w, torch.float16, "w")
+    _need(resid, torch.float32, "resid")
+    M, K = a.shape
+    N = w.shape[0]
+    x32 = resid if inplace else torch.empty(M, N, dtype=torch.float32, device=a.device)
+    x16 = torch.empty(M, N, dtype=torch.float16, device=a.device)
+    _check(lib().memvul_gemm_ln_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), gamma.data_ptr(),
+                                    beta.data_ptr(), eps, x32.data_ptr(), x16.data_ptr(), M, N, K, _stream()))
+    return x32, x16
 
 
 def attention_f16(qkv: torch.Tensor, lens: torch.Tensor, B: int, S: int, H: int) -> torch.Tensor:

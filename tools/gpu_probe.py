@@ -10,7 +10,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["gemm", "attention", "rowwise", "poolmatch", "encoder_tiny", "encoder_base", "model"]
+GROUPS = ["gemm", "gemm_ln", "attention", "rowwise", "poolmatch", "encoder_tiny", "encoder_base", "model"]
 
 
 def _report(name, got, ref, tol):
@@ -64,6 +64,47 @@ def g_gemm():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"  time gemm M={M} N={Nn} K={K} epi={epi}: {ms*1e3:.1f} us  {2.0*M*Nn*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    return ok
+
+
+def g_gemm_ln():
+    import torch
+    from memvul_b200 import native as N
+    ok = True
+    torch.manual_seed(5)
+    dev = "cuda"
+    for (M, K) in [(256, 768), (1000, 768), (4096, 3072), (20001, 768), (32768, 768), (32768, 3072)]:
+        a = torch.randn(M, K, device=dev).half()
+        w = (torch.randn(768, K, device=dev) * 0.05).half()
+        bias = torch.randn(768, device=dev)
+        resid = torch.randn(M, 768, device=dev) * 2 + 0.3
+        gamma = 1 + 0.1 * torch.randn(768, device=dev)
+        beta = 0.1 * torch.randn(768, device=dev)
+        ref = torch.nn.functional.layer_norm(a.float() @ w.float().T + bias + resid, (768,), gamma, beta, 1e-12)
+        x32, x16 = N.gemm_ln_f16(a, w, bias, resid, gamma, beta)
+        torch.cuda.synchronize()
+        ok &= _report(f"gemm_ln M={M} K={K} fp32", x32, ref, 2e-4)
+        ok &= _report(f"gemm_ln M={M} K={K} fp16", x16, ref, 4e-3)
+        buf = resid.clone()
+        y32, _ = N.gemm_ln_f16(a, w, bias, buf, gamma, beta, inplace=True)
+        torch.cuda.synchronize()
+        ok &= _report(f"gemm_ln M={M} K={K} in-place", y32, ref, 2e-4)
+    M = 32768
+    for K in (768, 3072):
+        a = torch.randn(M, K, device=dev).half()
+        w = (torch.randn(768, K, device=dev) * 0.05).half()
+        bias = torch.randn(768, device=dev); gamma = torch.ones(768, device=dev); beta = torch.zeros(768, device=dev)
+        resid = torch.randn(M, 768, device=dev)
+        for _ in range(3):
+            N.gemm_ln_f16(a, w, bias, resid, gamma, beta, inplace=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            N.gemm_ln_f16(a, w, bias, resid, gamma, beta, inplace=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"  time gemm_ln M={M} K={K}: {ms*1e3:.1f} us  {2.0*M*768*K/ms/1e9:.1f} TFLOP/s", flush=True)
     return ok
 
 
