@@ -337,10 +337,12 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
                                   mv::AttnCfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(first_tile_only ? 1 : (S + 127) / 128, H / 64, B);
+  const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
+  const int n_items = B * (H / 64) * n_qt;
+  const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, lens, reinterpret_cast<__half*>(ctx), S, H);
+      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
