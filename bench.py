@@ -17,6 +17,7 @@ One JSON line on rank 0:
   roofline   the tcgen05 GEMM kernel (dominant: ~70 % of the step): algorithmic FLOPs / live CUDA-event time
              vs MEASURED_PEAKS.json's sustained bf16 figure
   kernels    live per-kernel-class device time of one profiled step (CUDA events around every launch)
+  anchor_match  the match kernel alone on the bank-streaming regime (HBM GB/s) and on BASELINE config 4
   cpu_baseline  the CPU oracle (port of the reference's PyTorch path) timed on this box's host cores
 """
 from __future__ import annotations
@@ -48,6 +49,20 @@ def gemm_flops_per_step(batch: int, s: int) -> float:
     return 12.0 * 2.0 * m * (768 * 2304 + 768 * 768 + 768 * 3072 + 3072 * 768)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the GEMM kernels from the committed `ncu --set full` captures (profiles/ncu_traffic.json):
+    launch-weighted mean over the four GEMM launches of a layer.  None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        k = json.load(f)["kernels"]
+    names = ["gemm_qkv", "gemm_ffn_up", "ln_attn_out", "ln_ffn_down"]
+    if not all(n in k for n in names):
+        return None, None
+    return sum(k[n]["dram_traffic_bytes"] for n in names) / len(names), {n: k[n] for n in names}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -69,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -109,6 +124,46 @@ def pick_cpu_threads(probe) -> int:
                 best, best_t = c, dt
     torch.set_num_threads(best)
     return best
+
+
+def anchor_match_bench(dev, peaks):
+    """BASELINE metric part 2 ("anchor-match HBM GB/s"): memvul_pool_match (fused pool + header + match + softmax +
+    arg-max, one cooperative launch) timed alone, L2 evicted with clean lines between launches.
+      streaming : 1 query x 262,144 anchors (537 MB bank > L2) -- the HBM-bound regime
+      config4   : 256 queries x 16,384 anchors (BASELINE configs[3]) -- FP32-ALU bound, reported for completeness
+    Algorithmic bytes = 4*(G*512 + B*512 + 2*B*G) + 4*2*B*G (logits and probs are both written)."""
+    import torch
+    from memvul_b200 import native as N
+    H, D = 768, 512
+    out = {}
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(SEED)
+    for name, (B, G) in {"streaming": (1, 262144), "config4": (256, 16384)}.items():
+        cls = torch.randn(B, H, generator=g).to(dev)
+        wp, bp = (torch.randn(H, H, generator=g) * 0.03).to(dev), (torch.randn(H, generator=g) * 0.02).to(dev)
+        wh, bh = (torch.randn(D, H, generator=g) * 0.03).to(dev), (torch.randn(D, generator=g) * 0.02).to(dev)
+        wproj = (torch.randn(2, 3 * D, generator=g) * 0.03).to(dev)
+        bank = torch.relu(torch.randn(G, D, device=dev))
+        vterm = N.bank_prepare(bank, wproj)
+        ts = []
+        for i in range(8):
+            sink.copy_(flush[:1] + flush.sum())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            N.pool_match(cls, H, B, wp, bp, wh, bh, wproj, bank, vterm)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2] * 1e-3
+        nbytes = 4 * (G * D + B * D + 2 * B * G) + 4 * 2 * B * G
+        out[name] = {"queries": B, "anchors": G, "us": t * 1e6, "algorithmic_MB": nbytes / 1e6, "hbm_GBps": nbytes / t / 1e9,
+                     "frac_of_hbm_peak": nbytes / t / 1e9 / peaks["hbm_gbs"], "fp32_lane_Tinstr_per_s": 3.0 * B * G * D / t / 1e12}
+        del bank, vterm
+    out["peak_hbm_GBps"] = peaks["hbm_gbs"]
+    out["peak_src"] = peaks["src"]
+    return out
 
 
 def cpu_oracle_throughput(budget_s: float = 12.0, batch: int = 8):
@@ -282,6 +337,7 @@ def run_native(args):
     gemm_launches = sum(prof[k]["launches"] for k in prof if k.startswith("gemm_")) // prof_steps
     gflops = gemm_flops_per_step(B, SEQ)
     achieved = gflops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    traffic, traffic_detail = ncu_traffic()
     step_ms_prof = sum(v["ms"] for v in prof.values()) / prof_steps
     kernels = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "launches_per_step": v["launches"] // prof_steps,
                    "share": round(v["ms"] / prof_steps / step_ms_prof, 4) if step_ms_prof else None}
@@ -303,13 +359,18 @@ def run_native(args):
                                "peak": peaks["tflops_sustained"], "peak_src": peaks["src"] + " bf16 sustained"},
         "roofline": {"kernel": "gemm_f16_tcgen05_kernel (QKV, attn-out, FFN up/down; all 12 layers)", "bound": "tensor",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops_sustained"] if achieved else None, "traffic": None,
+                     "frac": achieved / peaks["tflops_sustained"] if achieved else None, "traffic": traffic,
+                     "traffic_src": "profiles/ncu_traffic.json: dram__bytes_read+write per launch, mean of the 4 GEMM kernels of a layer (ncu --set full)",
                      "peak_src": peaks["src"] + " (bf16 cuBLAS, sustained: kernel timed inside a long step)",
                      "flops_per_launch": gflops / gemm_launches if gemm_launches else None,
                      "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None, "launches_per_step": gemm_launches},
         "kernels": kernels,
         "clocks": clocks,
     }
+    if world == 1:
+        del model
+        torch.cuda.empty_cache()
+        line["anchor_match"] = anchor_match_bench(dev, peaks)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_oracle_throughput()
     print(json.dumps(line), flush=True)
@@ -320,7 +381,7 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

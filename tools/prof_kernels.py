@@ -1,6 +1,6 @@
 """Tiny harness for `ncu --set full`: runs ONE kernel class at the C2 shape a few times.
     ncu --set full --clock-control none --import-source on -k regex:<pat> -s 2 -c 1 -o gpurun_out/<name> \
-        python tools/prof_kernels.py <gemm_qkv|gemm_attn_out|gemm_ffn_up|gemm_ffn_down|attention|layernorm|pool_match>"""
+        python tools/prof_kernels.py <gemm_qkv|gemm_ffn_up|ln_attn_out|ln_ffn_down|attention|layernorm|pool_match>"""
 import os
 import sys
 
@@ -24,6 +24,14 @@ if which.startswith("gemm"):
     out = torch.empty(M, Nn, device=dev, dtype=torch.float32 if epi == 2 else torch.float16)
     for _ in range(iters):
         N.gemm_f16(a, w, bias, epi, resid=resid, out=out)
+elif which.startswith("ln_"):
+    K = {"ln_attn_out": 768, "ln_ffn_down": 3072}[which]
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(768, K, device=dev) * 0.05).half()
+    bias = torch.randn(768, device=dev); gamma = torch.ones(768, device=dev); beta = torch.zeros(768, device=dev)
+    resid = torch.randn(M, 768, device=dev)
+    for _ in range(iters):
+        N.gemm_ln_f16(a, w, bias, resid, gamma, beta, inplace=True)
 elif which == "attention":
     qkv = torch.randn(M, 3 * H, device=dev).half()
     lens = torch.full((B,), S, dtype=torch.int32, device=dev)
