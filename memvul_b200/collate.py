@@ -48,3 +48,16 @@ def batches(instances: List[Dict[str, Any]], batch_size: int):
     """``shuffle: false`` sequential batching (config_memory.json:50-57)."""
     for i in range(0, len(instances), batch_size):
         yield instances[i:i + batch_size]
+
+
+def plan_length_buckets(lengths: List[int], batch_size: int, window: int = 16) -> List[List[int]]:
+    """Batches of instance indices for a mixed-length stream (BASELINE config 5).  The reference pads every batch
+    to its longest member in data order, so one 512-token report makes 511 short ones pay for 512
+    tokens.  Here each window of ``window * batch_size`` consecutive instances is sorted by length before it is cut
+    into batches; results are re-ordered to data order by the caller, so the output is unchanged."""
+    out: List[List[int]] = []
+    span = max(1, window) * batch_size
+    for w0 in range(0, len(lengths), span):
+        idx = sorted(range(w0, min(len(lengths), w0 + span)), key=lambda i: (lengths[i], i))
+        out.extend(idx[i:i + batch_size] for i in range(0, len(idx), batch_size))
+    return out

@@ -46,7 +46,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                             int M, int N, int K, const float* __restrict__ bias, int store) {
+                             int M, int N, int K, const float* __restrict__ bias, int store, void* out_ptr) {
   using Cfg = Gemm2Cfg<EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -226,11 +226,13 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
           ++gc;
         } else {
           // fp16: two 32-column TMEM chunks fill one 32 x 64 staging box (128 B per row)
-          if ((c & 1) == 0 && store) {
+          const bool direct = (store == 2);          // experiment: 256-bit per-lane global stores, no smem staging
+          if ((c & 1) == 0 && store == 1) {
             if (lane == 0) bulk_wait_read_all();   // previous box has been read out of the staging buffer
             __syncwarp();
           }
           if (store) {
+            uint32_t pkd[16];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 b0 = *reinterpret_cast<const float4*>(bsm + 8 * u);
@@ -246,22 +248,36 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
               x[7] = __uint_as_float(v[8 * u + 7]) + b1.w;
               if constexpr (EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) x[t] = 0.5f * x[t] * (1.0f + erf_as(x[t] * 0.70710678118654752f));
+                for (int t = 0; t < 8; ++t) x[t] = gelu_erf_fast(x[t]);
               }
-              uint4 pk;
-              pk.x = pack_half2(x[0], x[1]);
-              pk.y = pack_half2(x[2], x[3]);
-              pk.z = pack_half2(x[4], x[5]);
-              pk.w = pack_half2(x[6], x[7]);
-              const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
-              *reinterpret_cast<uint4*>(my_row0 + ((unit ^ sw) << 4)) = pk;
+              pkd[4 * u + 0] = pack_half2(x[0], x[1]);
+              pkd[4 * u + 1] = pack_half2(x[2], x[3]);
+              pkd[4 * u + 2] = pack_half2(x[4], x[5]);
+              pkd[4 * u + 3] = pack_half2(x[6], x[7]);
             }
-            if (c & 1) {
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tmap_out, my_stg, col0 + (c >> 1) * 64, row0);
-                bulk_commit_group();
+            if (direct) {
+              const int grow = row0 + lane;
+              if (grow < M) {
+                __half* orow = reinterpret_cast<__half*>(out_ptr) + static_cast<size_t>(grow) * N + col0 + c * 32;
+                const uint32_t(&lo)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pkd[0]);
+                const uint32_t(&hi)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pkd[8]);
+                st_global_v8(orow, lo);
+                st_global_v8(orow + 16, hi);
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
+                *reinterpret_cast<uint4*>(my_row0 + ((unit ^ sw) << 4)) =
+                    make_uint4(pkd[4 * u], pkd[4 * u + 1], pkd[4 * u + 2], pkd[4 * u + 3]);
+              }
+              if (c & 1) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmap_out, my_stg, col0 + (c >> 1) * 64, row0);
+                  bulk_commit_group();
+                }
               }
             }
           }

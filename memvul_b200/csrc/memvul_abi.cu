@@ -227,6 +227,7 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
     attr_set = true;
   }
   static const bool nostore = getenv("MEMVUL_GEMM_NOSTORE") != nullptr;      // experiment: time the main loop alone
+  static const bool direct_st = getenv("MEMVUL_GEMM_DIRECT_ST") != nullptr;   // experiment: 256-bit per-lane stores
   CUtensorMap tout, tres;
   if (Cfg::RESID) {
     if (int rc = make_map(out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tout)) return rc;
@@ -239,7 +240,8 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   int clusters = sms / 2;
   if (tiles < clusters) clusters = tiles;
   LaunchScope ls(g_cls, st);
-  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias, nostore ? 0 : 1);   // __cluster_dims__(2,1,1)
+  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias,
+                                                              nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : 1), out);   // __cluster_dims__(2,1,1)
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
@@ -594,13 +596,20 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mv::pool_match_kernel, 256, 0));
-    if (blocks_per_sm < 1) return fail(MEMVUL_E_CUDA, "pool_match kernel does not fit on an SM");
-    if (blocks_per_sm > 4) blocks_per_sm = 4;
+  // Large problems (config-4 class) use the shared-memory tiled match: 1 block / SM with 167 KB of dynamic smem.
+  static const bool tiled_ok = [] { const char* e = getenv("MEMVUL_MATCH_TILED"); return !(e && strcmp(e, "0") == 0); }();
+  const bool tiled = tiled_ok && (phase_mask & MEMVUL_PM_MATCH) && D == mv::MatchTileCfg::D && B >= 32 &&
+                     static_cast<long long>(B) * G >= (1LL << 18);
+  const int dyn_smem = tiled ? mv::MatchTileCfg::SMEM_BYTES : 0;
+  static int blocks_per_sm[2] = {0, 0};
+  if (blocks_per_sm[tiled] == 0) {
+    if (tiled) CUDA_TRY(cudaFuncSetAttribute(mv::pool_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mv::pool_match_kernel, 256, dyn_smem));
+    if (n < 1) return fail(MEMVUL_E_CUDA, "pool_match kernel does not fit on an SM");
+    blocks_per_sm[tiled] = n > 4 ? 4 : n;
   }
-  const int grid = di.sms * blocks_per_sm;
+  const int grid = di.sms * blocks_per_sm[tiled];
   const int nwarps = grid * 8;
   mv::PoolMatchParams p;
   p.cls = cls; p.cls_stride = cls_stride;
@@ -608,7 +617,7 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   p.bank = bank; p.vterm = vterm; p.pooled = pooled; p.u = u; p.uterm = uterm;
   p.best_key = reinterpret_cast<unsigned long long*>(best_key);
   p.logits = logits; p.probs = probs; p.best_idx = best_idx; p.best_probs = best_probs;
-  p.B = B; p.G = G; p.H = H; p.D = D; p.same_idx = same_idx; p.phase_mask = phase_mask;
+  p.B = B; p.G = G; p.H = H; p.D = D; p.same_idx = same_idx; p.phase_mask = phase_mask; p.tiled = tiled ? 1 : 0;
   // b_chunk: aim at ~4 work items per resident warp so the tail is short, but keep each anchor quad's
   // registers alive across as many queries as possible.
   const long long units = static_cast<long long>(B) * ((G + 3) / 4);
@@ -622,9 +631,9 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   LaunchScope ls(KC_POOL_MATCH, st);
   if (multi) {
     void* args[] = {&p};
-    CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mv::pool_match_kernel), dim3(grid), dim3(256), args, 0, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mv::pool_match_kernel), dim3(grid), dim3(256), args, dyn_smem, st));
   } else {
-    mv::pool_match_kernel<<<grid, 256, 0, st>>>(p);
+    mv::pool_match_kernel<<<grid, 256, dyn_smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
   }
   return MEMVUL_OK;

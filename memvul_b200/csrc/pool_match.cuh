@@ -38,7 +38,7 @@ struct PoolMatchParams {
   float* probs;                          // [B,G,2]
   int* best_idx;                         // [B]
   float* best_probs;                     // [B,2]
-  int B, G, H, D, same_idx, b_chunk, phase_mask;
+  int B, G, H, D, same_idx, b_chunk, phase_mask, tiled;
 };
 
 // out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]).  Work item = (output column n, chunk of 8 rows b): the W row lives in
@@ -213,6 +213,137 @@ __device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled match for LARGE problems (BASELINE config 4: 256 queries x 16,384 anchors): the |u - v| term is O(B*G*512)
+// FP32 work, so what matters is operand reuse, like an SGEMM.  A block owns a 64-anchor tile of the bank in shared
+// memory (read from HBM exactly once per pass over the queries) and sweeps 64-query tiles against it, u arriving
+// in double-buffered 64-wide K chunks (cp.async); every thread keeps a 4 x 4 (query x anchor) register tile for
+// both classes.  Shared-memory rows are padded (+4 floats) so the 128-bit operand loads are conflict-free.
+struct MatchTileCfg {
+  static constexpr int BT = 64, GT = 64, KC = 64, D = 512;
+  static constexpr int V_LD = D + 4, U_LD = KC + 4;
+  static constexpr int OFF_V = 0;                                   // [GT][V_LD] floats
+  static constexpr int OFF_U = OFF_V + GT * V_LD * 4;               // [2][BT][U_LD]
+  static constexpr int OFF_WD = OFF_U + 2 * BT * U_LD * 4;          // [2][D]
+  static constexpr int SMEM_BYTES = OFF_WD + 2 * D * 4;             // 171,008 B
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = valid ? 16 : 0;                                    // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void match_phase_tiled(const PoolMatchParams& p, uint8_t* smem, unsigned long long* sbest) {
+  using T = MatchTileCfg;
+  float* sv = reinterpret_cast<float*>(smem + T::OFF_V);
+  float* su = reinterpret_cast<float*>(smem + T::OFF_U);
+  float* swd = reinterpret_cast<float*>(smem + T::OFF_WD);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int B = p.B, G = p.G;
+  const int n_bt = (B + T::BT - 1) / T::BT, n_gt = (G + T::GT - 1) / T::GT;
+  const int items = n_bt * n_gt;
+  // contiguous item ranges per block, anchor-tile major: consecutive items of a block share the bank tile
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per, it1 = min(items, it0 + per);
+  for (int i = tid; i < 2 * T::D; i += blockDim.x) swd[i] = p.wproj[(i / T::D) * 3 * T::D + 2 * T::D + (i % T::D)];
+  int cur_gt = -1;
+  for (int item = it0; item < it1; ++item) {
+    const int gt = item / n_bt, bt = item - gt * n_bt;
+    const int g0 = gt * T::GT, b0 = bt * T::BT;
+    __syncthreads();                                                // previous item is done with sv / su
+    if (gt != cur_gt) {                                             // stream this anchor tile in once
+      cur_gt = gt;
+      for (int c = tid; c < T::GT * (T::D / 4); c += blockDim.x) {
+        const int r = c / (T::D / 4), k4 = c % (T::D / 4);
+        const int g = g0 + r;
+        cp_async_16(sv + r * T::V_LD + k4 * 4, p.bank + static_cast<size_t>(min(g, G - 1)) * T::D + k4 * 4, g < G);
+      }
+    }
+    auto load_u = [&](int kc, int buf) {
+      for (int c = tid; c < T::BT * (T::KC / 4); c += blockDim.x) {
+        const int r = c / (T::KC / 4), k4 = c % (T::KC / 4);
+        const int b = b0 + r;
+        cp_async_16(su + (buf * T::BT + r) * T::U_LD + k4 * 4,
+                    p.u + static_cast<size_t>(min(b, B - 1)) * T::D + kc * T::KC + k4 * 4, b < B);
+      }
+      cp_async_commit();
+    };
+    load_u(0, 0);
+    float acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.f;
+    constexpr int NKC = T::D / T::KC;
+    for (int kc = 0; kc < NKC; ++kc) {
+      if (kc + 1 < NKC) { load_u(kc + 1, (kc + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncthreads();
+      const float* ub = su + ((kc & 1) * T::BT) * T::U_LD;
+#pragma unroll 4
+      for (int k4 = 0; k4 < T::KC / 4; ++k4) {
+        const int k = kc * T::KC + k4 * 4;
+        const float4 w0 = *reinterpret_cast<const float4*>(swd + k);
+        const float4 w1 = *reinterpret_cast<const float4*>(swd + T::D + k);
+        float4 uu[4], vv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) uu[i] = *reinterpret_cast<const float4*>(ub + (ty + 16 * i) * T::U_LD + k4 * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vv[j] = *reinterpret_cast<const float4*>(sv + (tx + 16 * j) * T::V_LD + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dx = fabsf(uu[i].x - vv[j].x), dy = fabsf(uu[i].y - vv[j].y);
+            const float dz = fabsf(uu[i].z - vv[j].z), dw = fabsf(uu[i].w - vv[j].w);
+            acc[i][j][0] = fmaf(dx, w0.x, fmaf(dy, w0.y, fmaf(dz, w0.z, fmaf(dw, w0.w, acc[i][j][0]))));
+            acc[i][j][1] = fmaf(dx, w1.x, fmaf(dy, w1.y, fmaf(dz, w1.z, fmaf(dw, w1.w, acc[i][j][1]))));
+          }
+      }
+      __syncthreads();                                              // everyone is done with this u buffer
+    }
+    // epilogue: + Wu.u + Wv.v, softmax, stores, per-query arg-max over this anchor tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + ty + 16 * i;
+      unsigned long long key = 0ull;
+      if (b < B) {
+        const float ut0 = p.uterm[b * 2 + 0], ut1 = p.uterm[b * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + tx + 16 * j;
+          if (g < G) {
+            const float l0 = acc[i][j][0] + ut0 + __ldg(p.vterm + g * 2 + 0);
+            const float l1 = acc[i][j][1] + ut1 + __ldg(p.vterm + g * 2 + 1);
+            const float m = fmaxf(l0, l1);
+            const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+            const float inv = 1.0f / (e0 + e1);
+            const float p0 = e0 * inv, p1 = e1 * inv;
+            const size_t o = (static_cast<size_t>(b) * G + g) * 2;
+            *reinterpret_cast<float2*>(p.logits + o) = make_float2(l0, l1);
+            *reinterpret_cast<float2*>(p.probs + o) = make_float2(p0, p1);
+            const float ps = p.same_idx == 0 ? p0 : p1;
+            const unsigned long long kk = (static_cast<unsigned long long>(__float_as_uint(ps)) << 32) |
+                                          static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(g));
+            key = max(key, kk);
+          }
+        }
+      }
+      // the 16 lanes sharing ty hold the other anchors of query b
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+      if (tx == 0 && b < B && key) {
+        if (sbest) atomicMax(sbest + b, key);
+        else atomicMax(p.best_key + b, key);
+      }
+    }
+  }
+}
+
 constexpr int kMaxSmemBest = 1024;     // queries per launch whose running arg-max lives in shared memory (8 KB)
 enum : int { PM_POOL = 1, PM_HEADER = 2, PM_UTERM = 4, PM_MATCH = 8, PM_FINAL = 16, PM_ALL = 31 };
 
@@ -260,7 +391,12 @@ __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p
       for (int b = threadIdx.x; b < p.B; b += blockDim.x) sbest[b] = 0ull;
       __syncthreads();
     }
-    match_phase(p, gwarp, nwarps, lane, sbest);
+    if (p.tiled) {
+      extern __shared__ __align__(16) uint8_t dyn_smem[];
+      match_phase_tiled(p, dyn_smem, sbest);
+    } else {
+      match_phase(p, gwarp, nwarps, lane, sbest);
+    }
     if (sbest) {
       __syncthreads();
       for (int b = threadIdx.x; b < p.B; b += blockDim.x)

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace mv {
 
@@ -333,6 +334,26 @@ __device__ __forceinline__ float max3(float a, float b, float c) {      // sm_10
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
+}
+// GELU(v) = v * Phi(v) = relu(v) - h(|v|),  h(a) = a * (0.5 * poly(t)) * t * exp(-a^2/2),  t = 1 / (1 + p' a),
+// i.e. the erf_as() evaluation with the 1/sqrt(2) input scaling folded into p' and the exponent constant, the 0.5
+// folded into the polynomial, and the sign handled by relu(): 15 instructions instead of 18.
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float a = fabsf(v);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, a, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx(a * a * (-0.5f * 1.4426950408889634f));
+  const float h = (p * t) * (e * a);
+  return fmaxf(v, 0.0f) - h;
+}
+// 256-bit global store (sm_100+, PTX 8.8): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 

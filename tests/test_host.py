@@ -178,6 +178,18 @@ def test_collate_pads_to_longest(tmp_path_factory, vocab_file):
     assert [len(b) for b in batches(inst, 3)] == [3, 1]
 
 
+def test_length_bucket_plan_is_a_permutation_with_less_padding():
+    from memvul_b200.collate import plan_length_buckets
+    g = torch.Generator().manual_seed(0)
+    lens = [int([128, 256, 512][i]) for i in torch.randint(0, 3, (1000,), generator=g)]
+    plan = plan_length_buckets(lens, 64, window=8)
+    assert sorted(i for b in plan for i in b) == list(range(1000)) and all(len(b) <= 64 for b in plan)
+    padded = lambda batches: sum(max(lens[i] for i in b) * len(b) for b in batches)
+    naive = [list(range(i, min(1000, i + 64))) for i in range(0, 1000, 64)]
+    assert padded(plan) < 0.7 * padded(naive)
+    assert padded(plan) >= sum(lens)
+
+
 def test_threshold_sweep_matches_reference_semantics():
     """custom_metric.py:35-52: thresholds np.arange(0.5, 0.9, 0.01); the LAST threshold reaching the best F1 wins."""
     rng = np.random.default_rng(0)

@@ -39,6 +39,27 @@ def test_gemm_tcgen05(N, M, Nn, K, epi):
         assert float((buf - ref).abs().max()) < 1e-3
 
 
+@pytest.mark.parametrize("M,K", [(256, 768), (1000, 768), (4096, 3072), (20001, 768)])
+def test_gemm_residual_layernorm_fused(N, M, K):
+    """SURVEY 2.2 K4/K6 in one kernel (six-CTA clusters): LayerNorm(A W^T + bias + resid) -> fp32 and fp16, also in place."""
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(768, K, device="cuda") * 0.05).half()
+    bias = torch.randn(768, device="cuda")
+    resid = torch.randn(M, 768, device="cuda") * 2 + 0.3
+    gamma = 1 + 0.1 * torch.randn(768, device="cuda")
+    beta = 0.1 * torch.randn(768, device="cuda")
+    ref = torch.nn.functional.layer_norm(a.float() @ w.float().T + bias + resid, (768,), gamma, beta, 1e-12)
+    x32, x16 = N.gemm_ln_f16(a, w, bias, resid, gamma, beta)
+    assert float((x32 - ref).abs().max()) < 2e-4
+    assert float((x16.float() - ref).abs().max()) < 4e-3
+    buf = resid.clone()
+    y32, y16 = N.gemm_ln_f16(a, w, bias, buf, gamma, beta, inplace=True)
+    assert torch.equal(y32, x32) and torch.equal(y16, x16)          # deterministic, in place == out of place
+    with pytest.raises(ValueError):
+        N.gemm_ln_f16(a[:128].contiguous(), w, bias, resid[:128].contiguous(), gamma, beta)
+
+
 def _attn_ref(qkv, lens, B, S, H):
     nH = H // 64
     q, k, v = qkv.float().view(B, S, 3, nH, 64).permute(2, 0, 3, 1, 4)

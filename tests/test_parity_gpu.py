@@ -240,3 +240,12 @@ def test_predict_driver_end_to_end(tmp_path_factory):
     assert "s_f1-score" in metrics and "accuracy" in metrics
     m = PM.cal_metrics(str(res), thres=0.5)
     assert m["TP"] + m["FN"] == 3 and m["TN"] + m["FP"] == 8
+    # length-bucketed batching writes the same file (rows are restored to data order)
+    res2 = d / "out_result_bucketed.json"
+    PM.test_siamese(str(d / "model.tar.gz"), str(d / "test_project.json"), str(d / "CWE_anchor_golden_project.json"),
+                    predictions_output_file=str(res2), batch_size=4, cuda_device=0, bucket_by_length=True)
+    lines2 = [json.loads(l) for l in res2.read_text().splitlines()]
+    assert [[r["Issue_Url"] for r in l] for l in lines2] == [[r["Issue_Url"] for r in l] for l in lines]
+    for la, lb in zip(lines, lines2):
+        for ra, rb in zip(la, lb):
+            assert all(abs(ra["predict"][k] - rb["predict"][k]) < 1e-5 for k in ra["predict"])
