@@ -36,10 +36,11 @@ struct GemmLnCfg {
 };
 
 __global__ void __cluster_dims__(6, 1, 1) __launch_bounds__(384, 1)
-gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a64,
+                           const __grid_constant__ CUtensorMap tmap_b,
                            const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x32,
                            const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast) {
   using Cfg = GemmLnCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -59,10 +60,12 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   const bool leader = half_m == 0;
 
   if (warp_idx == 0 && lane == 0) {
-    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_res); prefetch_tmap(&tmap_x32); prefetch_tmap(&tmap_x16);
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_a64); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_res); prefetch_tmap(&tmap_x32); prefetch_tmap(&tmap_x16);
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    // A multicast: a stage is rewritten by TMA loads issued in all three pairs, so it is free only when the MMAs of
+    // all three pairs have retired (3 multicast commits); unicast: only this pair's.
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], a_multicast ? Cfg::PAIRS : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], Cfg::PAIRS * Cfg::EPI_WARPS);     // 3 CTAs x 8 warps
@@ -94,7 +97,17 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
+          if (a_multicast) {
+            // The three pairs need the SAME 128 A rows per rank: pairs 0 and 1 each fetch 64 of them once and the TMA
+            // multicasts the box into all three CTAs of that rank -> a third of the A traffic out of L2.
+            if (pair < 2)
+              tma_load_2d_pair_mc(sa + pair * (Cfg::A_BYTES / 2), &tmap_a64, &full_bar[stage], kb * Cfg::BK,
+                                  row_a + static_cast<int>(pair) * 64,
+                                  static_cast<uint16_t>((1u << half_m) | (1u << (2 + half_m)) | (1u << (4 + half_m))),
+                                  kEvictNormal);
+          } else {
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
+          }
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -123,7 +136,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           for (int k = 0; k < Cfg::BK / 16; ++k)
             umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
                              (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], pair_mask);
+          umma_commit_pair(&empty_bar[stage], a_multicast ? static_cast<uint16_t>(0b111111) : pair_mask);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit_pair(&tfull_bar[acc], pair_mask);

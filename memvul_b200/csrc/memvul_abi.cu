@@ -310,8 +310,12 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
     if (n < 1) return fail(MEMVUL_E_CUDA, "fused GEMM+LayerNorm: no 6-CTA cluster fits on this device");
     max_clusters = n;
   }
-  CUtensorMap ta, tb, tres, t32, t16;
+  // TMA multicast of A across the three pairs works but measured 2-4 % slower than unicast (L2 already de-duplicates the
+  // three requests), so it is opt-in: MEMVUL_LN_MULTICAST=1.
+  static const bool a_mc = [] { const char* e = getenv("MEMVUL_LN_MULTICAST"); return e && strcmp(e, "1") == 0; }();
+  CUtensorMap ta, ta64, tb, tres, t32, t16;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
+  if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 64, &ta64)) return rc;
   if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, &tb)) return rc;
   if (int rc = make_map(resid, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tres)) return rc;
   if (int rc = make_map(x32, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &t32)) return rc;
@@ -319,7 +323,7 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   const int tiles = (M + Cfg::BM - 1) / Cfg::BM;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   LaunchScope ls(g_cls, st);
-  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tres, t32, t16, M, K, bias, gamma, beta, eps);
+  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, a_mc ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
