@@ -231,7 +231,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
             if (lane == 0) bulk_wait_read_all();   // previous box has been read out of the staging buffer
             __syncwarp();
           }
-          if (store) {
+          if (store && store != 4) {
             uint32_t pkd[16];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -271,7 +271,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                 *reinterpret_cast<uint4*>(my_row0 + ((unit ^ sw) << 4)) =
                     make_uint4(pkd[4 * u], pkd[4 * u + 1], pkd[4 * u + 2], pkd[4 * u + 3]);
               }
-              if (c & 1) {
+              if ((c & 1) && store != 3) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -279,6 +279,12 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                   bulk_commit_group();
                 }
               }
+            }
+          } else if (store == 4 && (c & 1)) {          // experiment: stores without the math / staging writes
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_out, my_stg, col0 + (c >> 1) * 64, row0);
+              bulk_commit_group();
             }
           }
         }

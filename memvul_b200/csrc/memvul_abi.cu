@@ -216,6 +216,12 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M
 }
 
 
+// experiment knob: MEMVUL_GEMM_EPI_MODE = 1 (default) | 3 (math + staging, no TMA store) | 4 (TMA store only)
+static int epi_mode() {
+  static const int m = [] { const char* e = getenv("MEMVUL_GEMM_EPI_MODE"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
 template <int EPI>
 int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
                      const float* resid, void* out, int sms, cudaStream_t st) {
@@ -241,7 +247,7 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   if (tiles < clusters) clusters = tiles;
   LaunchScope ls(g_cls, st);
   kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias,
-                                                              nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : 1), out);   // __cluster_dims__(2,1,1)
+                                                              nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode()), out);   // __cluster_dims__(2,1,1)
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }

@@ -26,6 +26,7 @@ try:  # pragma: no cover - AllenNLP is absent from the build image
     from allennlp.modules.token_embedders import TokenEmbedder  # type: ignore
     from allennlp.predictors import Predictor  # type: ignore
     from allennlp.training.metrics import Metric  # type: ignore
+    from allennlp.training.callbacks.callback import TrainerCallback  # type: ignore
     HAVE_ALLENNLP = True
 except Exception:  # noqa: BLE001
     HAVE_ALLENNLP = False
@@ -170,6 +171,25 @@ except Exception:  # noqa: BLE001
 
         def reset(self) -> None:
             raise NotImplementedError
+
+    class TrainerCallback(Registrable):
+        """``allennlp.training.callbacks.TrainerCallback``: only the hooks the reference's callbacks override."""
+
+        def __init__(self, serialization_dir: Optional[str] = None) -> None:
+            self.serialization_dir = serialization_dir
+            self.trainer = None
+
+        def on_start(self, trainer, is_primary: bool = True, **kwargs: Any) -> None:
+            self.trainer = trainer
+
+        def on_batch(self, trainer, *args: Any, **kwargs: Any) -> None:
+            pass
+
+        def on_epoch(self, trainer, metrics: Dict[str, Any], epoch: int, is_primary: bool = True, **kwargs: Any) -> None:
+            pass
+
+        def on_end(self, trainer, *args: Any, **kwargs: Any) -> None:
+            pass
 
 
 def registered(base: Type, name: str) -> type:

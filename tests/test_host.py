@@ -266,3 +266,42 @@ def test_load_archive_roundtrip(tmp_path, vocab_file):
     for k, v in arc.model.state_dict().items():
         assert torch.equal(v, sd[k]), k
     assert arc.dataset_reader._tokenizer.max_length == 256 and arc.validation_dataset_reader._tokenizer.max_length == 512
+
+
+def test_custom_validation_callback_refreshes_the_bank(tmp_path_factory, vocab_file):
+    """callbacks.py:43-53: on_epoch empties the memory, then re-encodes anchors[:128] and anchors[128:] through
+    forward_on_instances; registered under the reference's names."""
+    from memvul_b200.registrable import TrainerCallback
+    assert TrainerCallback.by_name("custom_validation").__name__ == "CustomValidation"
+    assert TrainerCallback.by_name("reset_dataloader").__name__ == "ResetLoader"
+    tmp_path = tmp_path_factory.mktemp("data")
+    reader, g, _, _ = _write_data(tmp_path, vocab_file)
+    reader.index_with(Vocabulary({"labels": ["same", "diff"]}))
+    many = {f"CWE-{i}": "buffer overflow" for i in range(130)}
+    (tmp_path / "big_golden_anchors.json").write_text(json.dumps(many))
+
+    class FakeModel:
+        def __init__(self):
+            self._golden_instances_embeddings, self._golden_instances_labels = "stale", ["stale"]
+            self.calls, self.evaled = [], False
+        def eval(self):
+            self.evaled = True
+        def forward_on_instances(self, inst):
+            assert self._golden_instances_labels is None or self._golden_instances_labels != ["stale"]
+            self.calls.append(len(inst))
+            self._golden_instances_labels = (self._golden_instances_labels or []) + [i["metadata"]["instance"][0]["label"] for i in inst]
+
+    class FakeTrainer:
+        pass
+    tr = FakeTrainer(); tr.model = FakeModel(); tr.data_loader = FakeTrainer(); tr.data_loader._instances = [1, 2]
+    cb = TrainerCallback.from_params({"type": "custom_validation", "anchor_path": str(tmp_path / "big_golden_anchors.json")},
+                                     data_reader=reader)
+    cb.on_epoch(tr, {}, 0, True)
+    assert tr.model.evaled and tr.model.calls == [128, 2] and len(tr.model._golden_instances_labels) == 130
+    assert tr.model._golden_instances_embeddings is None          # the fake never sets it: proves the reset happened
+    cb.on_epoch(tr, {}, 1, True)
+    assert tr.model.calls == [128, 2, 128, 2] and len(tr.model._golden_instances_labels) == 130
+    TrainerCallback.by_name("reset_dataloader")().on_epoch(tr, {}, 0, True)
+    assert tr.data_loader._instances is None
+    with pytest.raises(ValueError):
+        TrainerCallback.by_name("custom_validation")(anchor_path=g)

@@ -249,3 +249,61 @@ def test_predict_driver_end_to_end(tmp_path_factory):
     for la, lb in zip(lines, lines2):
         for ra, rb in zip(la, lb):
             assert all(abs(ra["predict"][k] - rb["predict"][k]) < 1e-5 for k in ra["predict"])
+
+
+def test_in_training_validation_entry_after_weight_update():
+    """custom_trainer.py:506-618 runs the `type == "test"` branch after callbacks.py:43-53 has rebuilt
+    the memory with the CURRENT weights.  An in-place parameter update (what an optimiser step does) must reach the
+    fp16 packed copy; bank, logits and the validation metrics are checked against the oracle on the updated weights."""
+    from memvul_b200.callbacks import CustomValidation
+    from memvul_b200.custom_metric import SiameseMeasureV1
+    from memvul_b200.synthetic import BERT_TINY, build_memory_model, synthetic_ids
+    from oracle import memvul_oracle as O
+    shape = BERT_TINY
+    model, _ = build_memory_model(shape, device="cuda")
+    alens = [9, 33, 64, 17, 40, 5, 64]
+    a_ids, a_mask, _ = synthetic_ids(len(alens), 64, lens=alens, seed=31, vocab_size=shape.vocab_size)
+    anchors = [{"sample1": {"token_ids": a_ids[i][a_mask[i]].tolist(), "type_ids": [0] * alens[i]}, "label": None,
+                "metadata": {"type": "golden", "instance": [{"label": f"CWE-{i}"}]}} for i in range(len(alens))]
+
+    class Reader:
+        def read(self, path):
+            return iter(anchors)
+
+    class Trainer:
+        pass
+    tr = Trainer(); tr.model = model
+    cb = CustomValidation("golden_anchors.json", data_reader=Reader())
+    cb.on_epoch(tr, {}, 0, True)
+    bank0 = model._golden_instances_embeddings.clone()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    with torch.no_grad():                                        # "optimiser step": every parameter moves in place
+        for p in model.parameters():
+            p.add_(torch.randn(p.shape, device=p.device, generator=g) * 0.02 * p.abs().mean().clamp_min(1e-3))
+    cb.on_epoch(tr, {}, 1, True)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref_bank = O.build_bank(sd, [(a_ids[i][a_mask[i]], a_mask[i][a_mask[i]]) for i in range(len(alens))], shape)
+    assert model._golden_instances_labels == [f"CWE-{i}" for i in range(len(alens))]
+    assert float((model._golden_instances_embeddings.cpu() - ref_bank).abs().max()) < TOL
+    assert float((model._golden_instances_embeddings - bank0).abs().max()) > 1e-4          # the refresh is not a no-op
+    lens = [64, 20, 3, 50, 64, 31]
+    ids, mask, tids = synthetic_ids(len(lens), 64, lens=lens, seed=32, vocab_size=shape.vocab_size)
+    label = torch.tensor([0, 1, 1, 0, 1, 1])                     # index into the labels namespace
+    with torch.no_grad():
+        out = model(sample1=_dev(ids, mask, tids), label=label.cuda(), metadata=_meta(len(lens), kind="test"))
+    ref = O.memory_forward(sd, ids, mask, tids, ref_bank, model._same_idx, shape)
+    assert float((out["native"]["device"]["logits"].cpu() - ref["logits"]).abs().max()) < TOL
+    got = model.get_metrics(reset=True)
+    # custom_metric.py:64-72 feeds (gold = label != "neg", probs[b][same_idx]); accuracy is over the arg-max anchor's [B,2]
+    meta = _meta(len(lens), kind="test")
+    want = SiameseMeasureV1(model._same_idx)
+    want(ref["probs"], meta)
+    w = want.get_metric(reset=True)
+    ps_got = torch.tensor(out["native"]["best_probs"].tolist())
+    assert float((ps_got - ref["probs"]).abs().max()) < TOL
+    margin = float((ref["probs"][:, 0] - ref["probs"][:, 1]).abs().min())
+    if margin > 2 * TOL:                                          # no sample sits on the decision boundary
+        assert got["accuracy"] == pytest.approx(float((ref["probs"].argmax(-1) == label).float().mean()))
+        assert got["s_thres"] == pytest.approx(w["thres"]) and got["s_f1-score"] == pytest.approx(w["f1"])
+        assert got["s_auc"] == pytest.approx(w["auc"], abs=1e-6)
+    print(f"validation entry: decision margin {margin:.3e}, accuracy {got['accuracy']:.3f}, s_thres {got['s_thres']}")
