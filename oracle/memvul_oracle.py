@@ -5,14 +5,25 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker
 or as the reported CPU baseline -- never as the thing shipped.
 
-PARITY UNPINNED: the reference (panshengyi/MemVul) ships no tests, golden
-vectors or fixtures for this path and cannot be
-imported in this image (AllenNLP 2.4.0 is absent).  The oracle is therefore
-pinned two ways instead:
+PARITY PINNED AGAINST THE REFERENCE RUN HERE (scope stated exactly): the reference
+(panshengyi/MemVul) ships no tests, golden vectors or fixtures for this path (SURVEY.md F2,
+section 8c), so there is nothing of its own to check against; instead the reference ITSELF is
+executed in the build container -- ``oracle/make_reference_golden.py`` imports the unmodified
+first-party files (MemVul/model_memory.py, MemVul/custom_PTM_embedder.py, MemVul/custom_metric.py,
+predict_memory.py) from /root/reference over stand-ins for the absent THIRD-PARTY packages
+(``oracle/ref_shim.py``: AllenNLP 2.4.0 layers restated from their documented behaviour, ``overrides``;
+``transformers.BertModel`` is 5.5 here instead of the pinned 4.1.0), runs them with the seeded
+synthetic weights and commits inputs + outputs as ``tests/golden/ref_*.{npz,json}``.
+``tests/test_reference_golden.py`` holds this oracle to those outputs (bank, header output, projector
+logits <= 2e-5, probabilities <= 2e-6, readable rows, metrics, cal_metrics), and
+``tests/test_parity_gpu.py::test_cuda_path_matches_the_reference_run`` holds the CUDA path to them.
+Not pinned by the reference: AllenNLP's own BertPooler / FeedForward / BasicTextFieldEmbedder /
+metric classes (stand-ins, see ref_shim.py) and the 4.1.0-vs-5.5 transformers difference.
+The oracle is additionally checked
   * against an independent implementation of the same third-party arithmetic
     (``transformers.BertModel`` eager attention; tests/test_oracle.py), and
   * against committed golden vectors it produced itself
-    (tests/golden/, made by oracle/make_golden.py) so drift is detected.
+    (tests/golden/{tiny_ragged,tiny_same1,base_small}.npz, made by oracle/make_golden.py) so drift is detected.
 
 What is restated (all fp32, plain PyTorch on CPU), with the reference lines:
   * ``bert_encoder``           HF transformers==4.1.0 ``BertModel`` as entered from

@@ -307,3 +307,66 @@ def test_in_training_validation_entry_after_weight_update():
         assert got["s_thres"] == pytest.approx(w["thres"]) and got["s_f1-score"] == pytest.approx(w["f1"])
         assert got["s_auc"] == pytest.approx(w["auc"], abs=1e-6)
     print(f"validation entry: decision margin {margin:.3e}, accuracy {got['accuracy']:.3f}, s_thres {got['s_thres']}")
+
+
+@pytest.mark.parametrize("name", ["ref_tiny_same0", "ref_tiny_same1", "ref_base", "ref_tiny_bank130"])
+def test_cuda_path_matches_the_reference_run(name, tmp_path):
+    """The drop-in against outputs of the REFERENCE's own files executed in the build container
+    (oracle/make_reference_golden.py): bank, u, logits, probs, human-readable rows, get_metrics, cal_metrics."""
+    from memvul_b200.predict_memory import cal_metrics
+    from memvul_b200.synthetic import BertShape, build_memory_model
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        j = json.load(f)
+    same = int(z["same_idx"])
+    model, _ = build_memory_model(BertShape(**j["shape"]), same_first=(j["label_vocab"][0] == "same"), device="cuda")
+    assert model._same_idx == same
+    a_ids, a_mask = torch.from_numpy(z["anchor_ids"]), torch.from_numpy(z["anchor_mask"])
+    G = a_ids.shape[0]
+    with torch.no_grad():
+        for c0, c1 in ((0, min(G, 128)), (128, G)):                     # predict_memory.py:81-83
+            if c0 >= c1:
+                continue
+            S = int(a_mask[c0:c1].sum(1).max())
+            assert model(sample1=_dev(a_ids[c0:c1, :S].contiguous(), a_mask[c0:c1, :S].contiguous()),
+                         metadata=[{"type": "golden", "instance": [{"label": l}]} for l in j["anchor_labels"][c0:c1]]) == {}
+        out = model(sample1=_dev(torch.from_numpy(z["ids"]), torch.from_numpy(z["mask"]), torch.from_numpy(z["type_ids"])),
+                    label=torch.from_numpy(z["label"]).cuda(), metadata=j["metadata"])
+    assert model._golden_instances_labels == j["anchor_labels"]
+    dev = out["native"]["device"]
+    errs = {"bank": float((model._golden_instances_embeddings.cpu() - torch.from_numpy(z["bank"])).abs().max()),
+            "u": float((dev["u"].cpu() - torch.from_numpy(z["u"])).abs().max()),
+            "logits": float((dev["logits"].cpu() - torch.from_numpy(z["logits"])).abs().max())}
+    p = np.asarray(out["probs"].tolist(), dtype=np.float32)
+    errs["p"] = float(np.abs(p - z["p"]).max())
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    ps = z["p"][:, :, same]
+    srt = np.sort(ps, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2 * TOL if G > 1 else np.ones(len(ps), bool)
+    got_idx = np.asarray(out["native"]["best_idx"].tolist())
+    assert (got_idx[clear] == ps.argmax(1)[clear]).all()
+    rows = model.make_output_human_readable(out)
+    for g, w in zip(rows, j["rows"]):
+        assert g["Issue_Url"] == w["Issue_Url"] and g["label"] == w["label"] and set(g["predict"]) == set(w["predict"])
+        assert max(abs(g["predict"][k] - w["predict"][k]) for k in w["predict"]) < TOL
+    best_ref = z["p"][np.arange(len(ps)), ps.argmax(1)]
+    if np.abs(best_ref[:, 0] - best_ref[:, 1]).min() > 2 * TOL:         # nobody on the arg-max boundary: exact metrics
+        m = model.get_metrics(reset=True)
+        for k in ("accuracy", "precision", "recall", "f1-score"):
+            assert m[k] == pytest.approx(j["metrics"][k], abs=1e-6), k
+        sweep = np.arange(0.5, 0.9, 0.01)                                # custom_metric.py:35-52 thresholds
+        if np.abs(best_ref[:, same][:, None] - sweep[None]).min() > TOL:  # no score within TOL of a sweep threshold
+            for k in ("s_precision", "s_recall", "s_f1-score", "s_thres"):
+                assert m[k] == pytest.approx(j["metrics"][k], abs=1e-6), k
+        order_gap = np.diff(np.sort(best_ref[:, same])).min() if len(best_ref) > 1 else 1.0
+        if order_gap > 2 * TOL:                                           # ranking metrics depend on the order only
+            assert m["s_auc"] == pytest.approx(j["metrics"]["s_auc"], abs=1e-9)
+    f = tmp_path / "golden_result.json"
+    f.write_text(json.dumps(rows[:2]) + "\n" + json.dumps(rows[2:]) + "\n")
+    for thres, ref in j["cal_metrics"].items():
+        vote_ref = np.max(ps, axis=1)
+        if np.abs(vote_ref - float(thres)).min() > TOL:
+            got = cal_metrics(str(f), thres=float(thres))
+            for k in ("TP", "FN", "TN", "FP", "f1"):
+                assert got[k] == pytest.approx(ref[k]), (thres, k)
