@@ -10,6 +10,8 @@ files are loaded unmodified from /root/reference:
     MemVul/custom_PTM_embedder.py PretrainedTransformerEmbedder.__init__ / forward (:172-242) over transformers.BertModel
     MemVul/custom_metric.py       SiameseMeasureV1, find_best_thres, cal_f1
     predict_memory.py             cal_metrics (:159-197), model_measure (:117-156)
+    MemVul/model_single.py        ModelSingle.__init__ / forward (:76-98) / make_output_human_readable / get_metrics
+    MemVul/reader_memory.py       ReaderMemory.__init__ / read_dataset / _read eval branches / text_to_instance
 The weights are the seeded synthetic state_dict (memvul_b200/synthetic.py, seed 2021) loaded through the reference
 model's own `load_state_dict`, i.e. under the reference's parameter names; inputs are the seeded synthetic ids.  What
 is stored per case: inputs, the anchor bank, the header output u, the projector logits (forward hooks), `output_dict
@@ -42,6 +44,14 @@ CASES = {
     # 130 anchors: the memory is built as 128 + 2 (predict_memory.py:81-83), longest anchor differs per chunk
     "ref_tiny_bank130": (dict(vocab_size=1024, hidden=128, layers=2, heads=2, intermediate=512, max_pos=512, header=512),
                          [30, 11, 24], 30, [5 + (7 * i) % 28 for i in range(128)] + [40, 6], ["same", "diff"]),
+}
+
+
+# MemVul-m (model_single.py), config C1 shape B=4, S=128: name -> (shape kwargs, lengths, S, class_labels order)
+SINGLE_CASES = {
+    "ref_single_tiny": (dict(vocab_size=1024, hidden=128, layers=2, heads=2, intermediate=512, max_pos=512, header=512),
+                        [128, 9, 64, 100], 128, ["neg", "pos"]),
+    "ref_single_c1": (dict(), [128, 9, 64, 100], 128, ["pos", "neg"]),
 }
 
 
@@ -130,10 +140,101 @@ def run_case(name: str) -> None:
     print(f"{name}: bank {tuple(bank.shape)} p {p.shape} same_idx {model._same_idx} metrics {json.dumps(metrics, default=float)[:120]}")
 
 
+def run_single_case(name: str) -> None:
+    """MemVul/model_single.py: ModelSingle.forward (:76-98), make_output_human_readable (:100-110), get_metrics."""
+    import importlib
+    from memvul_b200.synthetic import BertShape, synthetic_ids, synthetic_state_dict
+    import transformers
+    from oracle import ref_shim
+    kw, lens, S, label_vocab = SINGLE_CASES[name]
+    shape = BertShape(**kw)
+    ref_shim.install(hidden=shape.hidden, vocab_size=shape.vocab_size)
+    _, emb_mod, _, _ = ref_shim.import_reference(REFERENCE)
+    ms = importlib.import_module("MemVul.model_single")
+    sd = synthetic_state_dict(shape, model="single")
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg = transformers.BertConfig(vocab_size=shape.vocab_size, hidden_size=shape.hidden, num_hidden_layers=shape.layers,
+                                      num_attention_heads=shape.heads, intermediate_size=shape.intermediate,
+                                      max_position_embeddings=shape.max_pos, type_vocab_size=shape.type_vocab,
+                                      layer_norm_eps=shape.ln_eps, hidden_act="gelu")
+        transformers.BertModel(cfg).save_pretrained(os.path.join(tmp, "out_wwm"))
+        embedder = emb_mod.PretrainedTransformerEmbedder(model_name="bert-base-uncased",
+                                                        pretrained_model_path=os.path.join(tmp, "out_wwm"))
+    vocab = ref_shim.Vocabulary({"class_labels": label_vocab})
+    model = ms.ModelSingle(vocab, ref_shim.BasicTextFieldEmbedder({"tokens": embedder}), dropout=0.1, device="cpu")
+    own = model.state_dict()
+    unexpected = sorted(set(sd) - set(own))
+    missing = sorted(k for k in set(own) - set(sd) if not k.endswith("position_ids"))
+    assert not unexpected and not missing, (unexpected, missing)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    cap = {}
+    model._projector.register_forward_hook(lambda m, i, o: cap.__setitem__("logits", o.detach().clone()))
+    B = len(lens)
+    ids, mask, tids = synthetic_ids(B, S, lens=lens, vocab_size=shape.vocab_size)
+    rep = ["neg", "pos", "pos", "neg"]
+    label = torch.tensor([vocab.get_token_index(l, "class_labels") for l in rep])
+    meta = [{"instance": {"Issue_Url": f"https://example.test/issue/{i}", "label": rep[i]}} for i in range(B)]
+    with torch.no_grad():
+        out = model(_tokens(ids, mask, tids), label=label, metadata=meta)
+    rows = model.make_output_human_readable(out)
+    metrics = model.get_metrics(reset=True)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), ids=ids.numpy(), mask=mask.numpy(), type_ids=tids.numpy(),
+                        label=label.numpy(), logits=cap["logits"].numpy(), probs=np.asarray(out["probs"], dtype=np.float32),
+                        loss=np.float32(out["loss"]))
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump({"shape": kw, "label_vocab": label_vocab, "metadata": meta, "rows": rows, "metrics": metrics,
+                   "versions": {"torch": torch.__version__, "transformers": transformers.__version__,
+                                "reference_files": ["MemVul/model_single.py", "MemVul/custom_PTM_embedder.py"]}},
+                  f, indent=1, default=float)
+    print(f"{name}: probs {np.asarray(out['probs']).round(4).tolist()} loss {float(out['loss']):.6f}")
+
+
+def run_reader_case(name: str = "ref_reader") -> None:
+    """MemVul/reader_memory.py: __init__ (:38-71), read_dataset (:73-113), _read eval branches (:138-162),
+    text_to_instance (:195-246), over the toy vocabulary / data files the host tests use (tests/toy_vocab.py)."""
+    import importlib
+    from oracle import ref_shim
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from toy_vocab import TOY_VOCAB, write_toy_data
+    ref_shim.install()
+    ref_shim.import_reference(REFERENCE)
+    rm = importlib.import_module("MemVul.reader_memory")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        vocab_file = os.path.join(tmp, "vocab.txt")
+        with open(vocab_file, "w") as f:
+            f.write("\n".join(TOY_VOCAB) + "\n")
+        paths = write_toy_data(tmp)                                   # golden / test / validation / CVE dict
+        cwd = os.getcwd()
+        os.chdir(tmp)                                                 # the reference opens "xxx" + "CVE_dict.json" (:64-66)
+        try:
+            os.replace(paths["cve"], os.path.join(tmp, "xxxCVE_dict.json"))
+            tok = ref_shim.PretrainedTransformerTokenizer(vocab_file, add_special_tokens=True, max_length=16)
+            reader = rm.ReaderMemory(tokenizer=tok, target="Security_Issue_Full", anchor_path=paths["golden"], sample_neg=0.1,
+                                     token_indexers={"tokens": ref_shim.PretrainedTransformerIndexer(vocab_file, namespace="tags")})
+            for kind in ("golden", "test", "validation"):
+                rows = []
+                for inst in reader.read(paths[kind]):
+                    f = inst.fields
+                    idx = f["sample1"]._token_indexers["tokens"].tokens_to_indices(f["sample1"].tokens)
+                    rows.append({"tokens": [t.text for t in f["sample1"].tokens], "token_ids": idx["token_ids"],
+                                 "type_ids": idx["type_ids"], "label": f["label"].label if "label" in f else None,
+                                 "metadata": f["metadata"].metadata})
+                out[kind] = rows
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump({"instances": out, "reference_files": ["MemVul/reader_memory.py", "MemVul/util.py"]}, f, indent=1)
+    print(name, {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     import subprocess
-    if len(sys.argv) > 1:
-        run_case(sys.argv[1])
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_reader":
+        run_reader_case()
+    elif len(sys.argv) > 1:
+        (run_single_case if sys.argv[1] in SINGLE_CASES else run_case)(sys.argv[1])
     else:                           # one process per case: ref_shim.SETTINGS and the reference modules are per-process
-        for name in CASES:
+        for name in list(CASES) + list(SINGLE_CASES) + ["ref_reader"]:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), name])

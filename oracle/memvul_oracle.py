@@ -9,8 +9,8 @@ PARITY PINNED AGAINST THE REFERENCE RUN HERE (scope stated exactly): the referen
 (panshengyi/MemVul) ships no tests, golden vectors or fixtures for this path (SURVEY.md F2,
 section 8c), so there is nothing of its own to check against; instead the reference ITSELF is
 executed in the build container -- ``oracle/make_reference_golden.py`` imports the unmodified
-first-party files (MemVul/model_memory.py, MemVul/custom_PTM_embedder.py, MemVul/custom_metric.py,
-predict_memory.py) from /root/reference over stand-ins for the absent THIRD-PARTY packages
+first-party files (MemVul/model_memory.py, MemVul/model_single.py, MemVul/custom_PTM_embedder.py,
+MemVul/custom_metric.py, MemVul/reader_memory.py, predict_memory.py) from /root/reference over stand-ins for the absent THIRD-PARTY packages
 (``oracle/ref_shim.py``: AllenNLP 2.4.0 layers restated from their documented behaviour, ``overrides``;
 ``transformers.BertModel`` is 5.5 here instead of the pinned 4.1.0), runs them with the seeded
 synthetic weights and commits inputs + outputs as ``tests/golden/ref_*.{npz,json}``.

@@ -15,7 +15,9 @@ What is real and what is a stand-in during such a run:
   * stand-ins written here from AllenNLP 2.4.0's documented behaviour (the package is absent):
     `Registrable.register`, `Model`, `Vocabulary`, `BasicTextFieldEmbedder` (kwargs routed by the embedder's forward
     signature), `BertPooler` (= dropout(HF BertPooler(tokens))), `FeedForward` (= dropout(act(linear(x))) per layer),
-    `CategoricalAccuracy`, `FBetaMeasure`, `PretrainedTransformerTokenizer` (special-token counts only),
+    `CategoricalAccuracy`, `FBetaMeasure`, `PretrainedTransformerTokenizer` (special-token counts; WordPiece via the
+    `tokenizers` library when given a vocab file), `PretrainedTransformerIndexer`, `DatasetReader.read`, `TextField` /
+    `LabelField` / `MetadataField` / `Instance` (plain holders),
     `InitializerApplicator` (no-op), and `overrides` (identity decorator).  Every other name the reference merely
     imports (`matplotlib`, `spacy`, trainer classes, ...) resolves to an inert placeholder.
 """
@@ -219,13 +221,73 @@ class _HFTokenizerStub:
         return SETTINGS["vocab_size"]
 
 
-class PretrainedTransformerTokenizer(Registrable):
-    """Only what the embedder's constructor reads: vocabulary size and the [CLS] / [SEP] counts."""
+class Token:
+    def __init__(self, text: str, text_id: int, type_id: int = 0) -> None:
+        self.text, self.text_id, self.type_id = text, text_id, type_id
 
-    def __init__(self, model_name: str, *a: Any, **k: Any) -> None:
+
+class Tokenizer(Registrable):
+    pass
+
+
+class PretrainedTransformerTokenizer(Tokenizer):
+    """With a hub name: only what the embedder's constructor reads (vocabulary size, [CLS] / [SEP] counts).
+    With a path to a vocab.txt: BERT WordPiece through the `tokenizers` library -- the backend of the HF fast
+    tokenizer AllenNLP wraps -- lower-cased, [CLS] ... [SEP] added, truncated to max_length."""
+
+    def __init__(self, model_name: str, add_special_tokens: bool = True, max_length: Optional[int] = None,
+                 tokenizer_kwargs: Optional[Dict[str, Any]] = None, **k: Any) -> None:
+        import os
         self.tokenizer = _HFTokenizerStub()
         self.single_sequence_start_tokens = ["[CLS]"]
         self.single_sequence_end_tokens = ["[SEP]"]
+        self._wp = None
+        if os.path.isfile(model_name):
+            import tokenizers
+            self._wp = tokenizers.BertWordPieceTokenizer(model_name, lowercase=True)
+            if max_length is not None:
+                self._wp.enable_truncation(max_length=max_length)
+            self._special = add_special_tokens
+
+    def tokenize(self, text: str) -> List[Token]:
+        enc = self._wp.encode(text, add_special_tokens=self._special)
+        return [Token(t, i, ty) for t, i, ty in zip(enc.tokens, enc.ids, enc.type_ids)]
+
+
+class PretrainedTransformerIndexer(Registrable):
+    def __init__(self, model_name: str, namespace: str = "tags", max_length: Optional[int] = None, **k: Any) -> None:
+        self._namespace = namespace
+
+    def tokens_to_indices(self, tokens: List[Token], vocabulary: Any = None) -> Dict[str, List[Any]]:
+        return {"token_ids": [t.text_id for t in tokens], "mask": [True] * len(tokens), "type_ids": [t.type_id for t in tokens]}
+
+
+class TextField:
+    def __init__(self, tokens: List[Token], token_indexers: Dict[str, Any] = None) -> None:
+        self.tokens, self._token_indexers = tokens, token_indexers
+
+
+class LabelField:
+    def __init__(self, label: Any, label_namespace: str = "labels", skip_indexing: bool = False) -> None:
+        self.label, self._label_namespace = label, label_namespace
+
+
+class MetadataField:
+    def __init__(self, metadata: Any) -> None:
+        self.metadata = metadata
+
+
+class Instance:
+    def __init__(self, fields: Dict[str, Any]) -> None:
+        self.fields = fields
+
+
+class DatasetReader(Registrable):
+    def __init__(self, *a: Any, **k: Any) -> None:
+        pass
+
+    def read(self, file_path: str):
+        yield from self._read(file_path)
 
 
 REAL: Dict[str, Dict[str, Any]] = {
@@ -239,7 +301,11 @@ REAL: Dict[str, Dict[str, Any]] = {
     "allennlp.modules.seq2vec_encoders": {"BertPooler": BertPooler},
     "allennlp.nn": {"InitializerApplicator": InitializerApplicator, "RegularizerApplicator": RegularizerApplicator},
     "allennlp.training.metrics": {"Metric": Metric, "CategoricalAccuracy": CategoricalAccuracy, "FBetaMeasure": FBetaMeasure},
-    "allennlp.data.tokenizers": {"PretrainedTransformerTokenizer": PretrainedTransformerTokenizer},
+    "allennlp.data.tokenizers": {"PretrainedTransformerTokenizer": PretrainedTransformerTokenizer, "Tokenizer": Tokenizer},
+    "allennlp.data.token_indexers": {"PretrainedTransformerIndexer": PretrainedTransformerIndexer},
+    "allennlp.data.dataset_readers.dataset_reader": {"DatasetReader": DatasetReader},
+    "allennlp.data.fields": {"TextField": TextField, "LabelField": LabelField, "MetadataField": MetadataField},
+    "allennlp.data.instance": {"Instance": Instance},
 }
 
 
@@ -285,6 +351,10 @@ def install(hidden: int = 768, vocab_size: int = 30522) -> None:
     SETTINGS["hidden"], SETTINGS["vocab_size"] = hidden, vocab_size
     if not any(isinstance(f, _Finder) for f in sys.meta_path):
         sys.meta_path.insert(0, _Finder())
+    # reader_memory.py imports a class transformers no longer ships (unused by the reader)
+    import transformers.utils.dummy_pt_objects as dummy
+    if not hasattr(dummy, "ElectraForMaskedLM"):
+        dummy.ElectraForMaskedLM = type("ElectraForMaskedLM", (), {})
     # numpy 2.x dropped the private paths predict_memory.py imports from (numpy.core.*, numpy.lib.npyio)
     import numpy as np
     for name, attrs in (("numpy.core.defchararray", {"encode": np.char.encode}), ("numpy.core.fromnumeric", {"sort": np.sort}),

@@ -118,22 +118,9 @@ def test_wordpiece_matches_hf_bert_tokenizer(vocab_file):
 
 
 def _write_data(tmp_path, vocab_file):
-    anchors = {"CWE-79": "sql injection in the parser", "CWE-120": "buffer overflow", "CWE-416": "use after free"}
-    g = tmp_path / "CWE_anchor_golden_project.json"
-    g.write_text(json.dumps(anchors))
-    cve = {"CVE-1": {"CWE_ID": "CWE-120", "CVE_Description": "x"}, "CVE-2": {"CWE_ID": "CWE-79", "CVE_Description": "x"},
-           "CVE-3": {"CWE_ID": None, "CVE_Description": "x"}}
-    c = tmp_path / "CVE_dict.json"
-    c.write_text(json.dumps(cve))
-    rows = [{"Issue_Url": "u0", "Issue_Title": "crash", "Issue_Body": "when url is null", "Security_Issue_Full": 0},
-            {"Issue_Url": "u1", "Issue_Title": "buffer overflow", "Issue_Body": "in the parser", "Security_Issue_Full": 1, "CVE_ID": "CVE-1"},
-            {"Issue_Url": "u2", "Issue_Title": "fixed", "Issue_Body": "a b", "Security_Issue_Full": "0"},
-            {"Issue_Url": "u3", "Issue_Title": "sql", "Issue_Body": "injection", "Security_Issue_Full": "1", "CVE_ID": "CVE-2"},
-            {"Issue_Url": "u4", "Issue_Title": "heap", "Issue_Body": "free", "Security_Issue_Full": 1, "CVE_ID": "CVE-3"}]
-    t = tmp_path / "test_project.json"
-    t.write_text(json.dumps(rows))
-    v = tmp_path / "validation_project.json"
-    v.write_text(json.dumps(rows))
+    from toy_vocab import write_toy_data
+    paths = write_toy_data(tmp_path)
+    g, c, t, v = paths["golden"], paths["cve"], paths["test"], paths["validation"]
     reader = DatasetReader.from_params({"type": "reader_memory", "target": "Security_Issue_Full",
                                         "tokenizer": {"type": "pretrained_transformer", "model_name": vocab_file,
                                                       "add_special_tokens": True, "max_length": 16},

@@ -370,3 +370,38 @@ def test_cuda_path_matches_the_reference_run(name, tmp_path):
             got = cal_metrics(str(f), thres=float(thres))
             for k in ("TP", "FN", "TN", "FP", "f1"):
                 assert got[k] == pytest.approx(ref[k]), (thres, k)
+
+
+@pytest.mark.parametrize("name", ["ref_single_tiny", "ref_single_c1"])
+def test_model_single_matches_the_reference_run(name):
+    """MemVul-m (config C1: B=4, S=128) against MemVul/model_single.py executed in the build container."""
+    from memvul_b200.custom_PTM_embedder import PretrainedTransformerEmbedder
+    from memvul_b200.model_single import ModelSingle
+    from memvul_b200.modules import BasicTextFieldEmbedder
+    from memvul_b200.registrable import Vocabulary
+    from memvul_b200.synthetic import BertShape, config_lite, load_into, synthetic_state_dict
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        j = json.load(f)
+    shape = BertShape(**j["shape"])
+    emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape))
+    model = ModelSingle(Vocabulary({"class_labels": j["label_vocab"]}), BasicTextFieldEmbedder({"tokens": emb}))
+    load_into(model, synthetic_state_dict(shape, model="single"))
+    model.eval().cuda()
+    with torch.no_grad():
+        out = model(_dev(torch.from_numpy(z["ids"]), torch.from_numpy(z["mask"]), torch.from_numpy(z["type_ids"])),
+                    label=torch.from_numpy(z["label"]).cuda(), metadata=j["metadata"])
+    err = float((out["logits_device"].cpu() - torch.from_numpy(z["logits"])).abs().max())
+    assert err < TOL and float(np.abs(np.asarray(out["probs"]) - z["probs"]).max()) < TOL
+    assert float(out["loss"]) == pytest.approx(float(z["loss"]), abs=TOL)
+    rows = model.make_output_human_readable(out)
+    margin = float(np.abs(z["probs"][:, 0] - z["probs"][:, 1]).min())
+    for g, w in zip(rows, j["rows"]):
+        assert g["Issue_Url"] == w["Issue_Url"] and g["label"] == w["label"] and abs(g["prob"] - w["prob"]) < TOL
+        if margin > 2 * TOL:
+            assert g["predict"] == w["predict"]
+    if margin > 2 * TOL:
+        m = model.get_metrics(reset=True)
+        for k, v in j["metrics"].items():
+            assert m[k] == pytest.approx(v, abs=1e-6), k
+    print(f"{name}: logits err {err:.2e}, decision margin {margin:.2e}")

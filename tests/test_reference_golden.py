@@ -93,3 +93,48 @@ def test_fixture_provenance():
     for name in REF_CASES:
         _, j, _ = load_case(name)
         assert "MemVul/model_memory.py" in j["versions"]["reference_files"]
+
+
+@pytest.mark.parametrize("name", ["ref_single_tiny", "ref_single_c1"])
+def test_oracle_single_head_reproduces_the_reference_run(name):
+    """MemVul/model_single.py:76-98 executed from /root/reference (config C1 shape: B=4, S=128)."""
+    z, j, shape = load_case(name)
+    sd = O.synthetic_state_dict(shape, model="single")
+    ids, mask, tids = (torch.from_numpy(z[k]) for k in ("ids", "mask", "type_ids"))
+    with torch.no_grad():
+        out = O.single_forward(sd, ids, mask, tids, shape)
+    assert float((out["logits"] - torch.from_numpy(z["logits"])).abs().max()) < 2e-5
+    assert float((out["probs"] - torch.from_numpy(z["probs"])).abs().max()) < 2e-6
+    loss = torch.nn.functional.cross_entropy(out["logits"], torch.from_numpy(z["label"]))
+    assert float(loss) == pytest.approx(float(z["loss"]), abs=1e-6)
+    assert [r["predict"] for r in j["rows"]] == [j["label_vocab"][int(k)] for k in out["probs"].argmax(-1)]
+
+
+def test_host_reader_reproduces_the_reference_reader(tmp_path_factory):
+    """MemVul/reader_memory.py executed from /root/reference over the toy files (tests/toy_vocab.py): same instances,
+    same order, same word pieces, labels and metadata."""
+    from memvul_b200.registrable import DatasetReader, Vocabulary
+    from toy_vocab import TOY_VOCAB, write_toy_data
+    with open(os.path.join(GOLD, "ref_reader.json")) as f:
+        ref = json.load(f)["instances"]
+    tmp = tmp_path_factory.mktemp("data")                    # the dispatch is a substring test on the whole path
+    vocab_file = os.path.join(str(tmp), "vocab.txt")
+    with open(vocab_file, "w") as f:
+        f.write("\n".join(TOY_VOCAB) + "\n")
+    paths = write_toy_data(tmp)
+    reader = DatasetReader.from_params({"type": "reader_memory", "target": "Security_Issue_Full",
+                                        "tokenizer": {"type": "pretrained_transformer", "model_name": vocab_file,
+                                                      "add_special_tokens": True, "max_length": 16},
+                                        "token_indexers": {"tokens": {"type": "pretrained_transformer", "namespace": "tags"}},
+                                        "cve_dict_path": paths["cve"]})
+    labels = Vocabulary({"labels": ["same", "diff"]})
+    reader.index_with(labels)
+    for kind in ("golden", "test", "validation"):
+        got = list(reader.read(paths[kind]))
+        assert len(got) == len(ref[kind])
+        for g, w in zip(got, ref[kind]):
+            assert g["sample1"]["token_ids"] == w["token_ids"] and g["sample1"]["type_ids"] == w["type_ids"]
+            assert g["metadata"] == w["metadata"]
+            assert g.get("label_str") == w["label"]
+            if w["label"] is not None:
+                assert g["label"] == labels.get_token_index(w["label"], "labels")
