@@ -44,12 +44,13 @@ struct AttnCfg {
 
 __global__ void __launch_bounds__(AttnCfg::THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
-                         const int* __restrict__ lens, __half* __restrict__ ctx, int B, int S, int H, int n_qt) {
+                         const int* __restrict__ lens, __half* __restrict__ ctx, int B, int S, int H, int n_qt, int wait_mode) {
   using C = AttnCfg;
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
   const int n_heads = H / C::DH;
   const int n_items = B * n_heads * n_qt;                  // n_qt = query tiles per sequence that are computed
+  const int idle_tma = wait_mode & 3, idle_mma = (wait_mode >> 2) & 3, idle_sm = (wait_mode >> 4) & 3;   // see mbar_wait_idle
 
   extern __shared__ __align__(1024) uint8_t smem[];        // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -111,12 +112,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         if (q0 >= len) continue;
         const int nkb = (len + C::BKV - 1) / C::BKV;
         const int row_base = b * S;
-        mbar_wait(q_empty, (it & 1u) ^ 1u);                    // previous item's last Q K^T has retired
+        mbar_wait_idle(q_empty, (it & 1u) ^ 1u, idle_tma);     // previous item's last Q K^T has retired
         mbar_arrive_expect_tx(q_full, C::Q_BYTES);
         tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_base + q0, kEvictFirst);
         for (int j = 0; j < nkb; ++j, ++g) {
           const uint32_t st = g % C::KV_STAGES;
-          mbar_wait(&kv_empty[st], ((g / C::KV_STAGES) & 1u) ^ 1u);
+          mbar_wait_idle(&kv_empty[st], ((g / C::KV_STAGES) & 1u) ^ 1u, idle_tma);
           const int row_k = row_base + j * C::BKV;
           mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
           tma_load_2d(smem + C::OFF_K + st * C::KV_BYTES, &tmap_kv, &k_full[st], H + h * C::DH, row_k, kEvictLast);
@@ -141,7 +142,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         auto issue_qk = [&](int j) {
           const uint32_t g = g0 + static_cast<uint32_t>(j);
           const uint32_t st = g % C::KV_STAGES;
-          mbar_wait(&k_full[st], (g / C::KV_STAGES) & 1u);
+          mbar_wait_idle(&k_full[st], (g / C::KV_STAGES) & 1u, idle_mma);
           tc_fence_after();
           const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + st * C::KV_BYTES));
           const uint32_t d = tmem_base + C::TM_S + (g & 1u) * C::BKV;
@@ -152,16 +153,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           umma_commit(&s_full[g & 1u]);
           if (j == nkb - 1) umma_commit(q_empty);              // Q may be overwritten once this product retires
         };
-        mbar_wait(q_full, it & 1u);
+        mbar_wait_idle(q_full, it & 1u, idle_mma);
         // S[g&1] of the first two blocks is free: the previous item's last two p_full phases were waited on below.
         issue_qk(0);
         if (nkb > 1) issue_qk(1);
         for (int j = 0; j < nkb; ++j) {
           const uint32_t g = g0 + static_cast<uint32_t>(j);
           const uint32_t st = g % C::KV_STAGES;
-          mbar_wait(&p_full[g & 1u], (g >> 1) & 1u);           // P_g in smem, S[g&1] drained, O rescaled
-          if (j == 0) mbar_wait(o_free, (it & 1u) ^ 1u);       // previous item's O has been read out
-          mbar_wait(&v_full[st], (g / C::KV_STAGES) & 1u);
+          mbar_wait_idle(&p_full[g & 1u], (g >> 1) & 1u, idle_mma);   // P_g in smem, S[g&1] drained, O rescaled
+          if (j == 0) mbar_wait_idle(o_free, (it & 1u) ^ 1u, idle_mma);   // previous item's O has been read out
+          mbar_wait_idle(&v_full[st], (g / C::KV_STAGES) & 1u, idle_mma);
           tc_fence_after();
           const uint32_t p_addr = smem_u32(smem + C::OFF_P + (g & 1u) * C::P_BYTES);
           const uint32_t v_addr = smem_u32(smem + C::OFF_V + st * C::KV_BYTES);
@@ -203,7 +204,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       const int nkb = (len + C::BKV - 1) / C::BKV;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkb; ++j, ++g) {
-        mbar_wait(&s_full[g & 1u], (g >> 1) & 1u);
+        mbar_wait_idle(&s_full[g & 1u], (g >> 1) & 1u, idle_sm);
         tc_fence_after();
         uint32_t s[2][32];
         const uint32_t s_addr = tmem_base + lane_addr + C::TM_S + (g & 1u) * C::BKV;
@@ -263,7 +264,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const float alpha = ex2_approx((m_run - m_new) * c);   // 0 on the first block (m_run = -inf), else 1 unless grown
         if (j > 0) {
-          mbar_wait(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);   // O holds blocks 0..j-1 of this item
+          mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);   // O holds blocks 0..j-1 of this item
           tc_fence_after();
           if (any_grow) {
 #pragma unroll
@@ -287,7 +288,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         if (lane == 0) mbar_arrive(&p_full[g & 1u]);
       }
       // ---------------- O / l -> ctx ----------------
-      mbar_wait(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+      mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int q = q0 + r;

@@ -58,6 +58,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   const uint32_t half_m = cta_rank & 1u;                   // which 128 rows of the 256-row tile
   const uint32_t leader_rank = cta_rank & ~1u;
   const bool leader = half_m == 0;
+  const int idle_tma = (a_multicast >> 4) & 3, idle_mma = (a_multicast >> 6) & 3, idle_epi = (a_multicast >> 8) & 3;   // mbar_wait_idle modes of the single-lane warps
+  a_multicast &= 1;
 
   if (warp_idx == 0 && lane == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_a64); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_res); prefetch_tmap(&tmap_x32); prefetch_tmap(&tmap_x16);
@@ -94,7 +96,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int row_a = tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait_idle(&empty_bar[stage], phase ^ 1u, idle_tma);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           if (a_multicast) {
@@ -123,11 +125,11 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_idle(&tempty_bar[acc], acc_phase ^ 1u, idle_mma);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_idle(&full_bar[stage], phase, idle_mma);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(sa);
@@ -177,7 +179,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     uint32_t acc_phase = 0, gc = 0, it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int row0 = strip_row0(tile);
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_idle(&tfull_bar[acc], acc_phase, idle_epi);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               static_cast<uint32_t>(acc * Cfg::BN + half_sel * 128);
@@ -191,7 +193,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&a)[32] = r[c & 1];
         uint8_t* rowp = ((c & 1) ? buf1 : buf0) + lane * 128;
-        mbar_wait(&my_res_bar[c & 1], (gc >> 1) & 1u);
+        mbar_wait_idle(&my_res_bar[c & 1], (gc >> 1) & 1u, idle_epi);
         ++gc;
         uint32_t v[32];
 #pragma unroll

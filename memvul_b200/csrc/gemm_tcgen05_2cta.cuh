@@ -61,6 +61,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
   const int lane = static_cast<int>(threadIdx.x & 31);
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
+  const int idle_tma = (store >> 8) & 3, idle_mma = (store >> 10) & 3, idle_epi = (store >> 12) & 3;     // how the single-lane warps wait (mbar_wait_idle)
+  store &= 0xff;
 
   if (warp_idx == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -106,7 +108,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         const int row_a = m_blk * Cfg::BM + static_cast<int>(cta_rank) * Cfg::BM_CTA;
         const int row_b = n_blk * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait_idle(&empty_bar[stage], phase ^ 1u, idle_tma);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
@@ -124,11 +126,11 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_idle(&tempty_bar[acc], acc_phase ^ 1u, idle_mma);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_idle(&full_bar[stage], phase, idle_mma);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(sa);
@@ -185,7 +187,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
       // bias slice of this warp -> smem (independent of the accumulator: overlaps the wait below)
       *reinterpret_cast<float4*>(my_bias + lane * 4) = __ldg(reinterpret_cast<const float4*>(bias + col0) + lane);
       __syncwarp();
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_idle(&tfull_bar[acc], acc_phase, idle_epi);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               static_cast<uint32_t>(acc * Cfg::BN + half_sel * COLS_PER_WARP);
@@ -201,7 +203,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
           const uint32_t b = gc & 1u;
           uint8_t* rowp = my_row0 + b * Cfg::STG_BYTES;
           if (store) {
-            mbar_wait(&my_res_bar[b], (gc >> 1) & 1u);              // residual chunk has landed
+            mbar_wait_idle(&my_res_bar[b], (gc >> 1) & 1u, idle_epi);   // residual chunk has landed
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               float4* p = reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(u) ^ sw) << 4));

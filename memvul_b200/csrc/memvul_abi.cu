@@ -216,6 +216,13 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M
 }
 
 
+// MEMVUL_GEMM_WAIT (default 5 = suspend-hinted TMA + MMA warps: r01n, -2..4 % on QKV / FFN-up): how the GEMM kernels' single-lane TMA / MMA warps wait (bits 0-1 TMA warp, bits 2-3 MMA warp, bits 4-5
+// epilogue warps; 0 spin, 1 suspend hint, 2 hint + nanosleep -- ptx.cuh mbar_wait_idle)
+static int gemm_wait_mode() {
+  static const int m = [] { const char* e = getenv("MEMVUL_GEMM_WAIT"); return e ? atoi(e) & 63 : 5; }();
+  return m;
+}
+
 // experiment knob: MEMVUL_GEMM_EPI_MODE = 1 (default) | 3 (math + staging, no TMA store) | 4 (TMA store only)
 static int epi_mode() {
   static const int m = [] { const char* e = getenv("MEMVUL_GEMM_EPI_MODE"); return e ? atoi(e) : 1; }();
@@ -247,7 +254,7 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   if (tiles < clusters) clusters = tiles;
   LaunchScope ls(g_cls, st);
   kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias,
-                                                              nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode()), out);   // __cluster_dims__(2,1,1)
+                                                              (nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode())) | (gemm_wait_mode() << 8), out);   // __cluster_dims__(2,1,1)
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
@@ -329,9 +336,16 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   const int tiles = (M + Cfg::BM - 1) / Cfg::BM;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   LaunchScope ls(g_cls, st);
-  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, a_mc ? 1 : 0);
+  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (gemm_wait_mode() << 4));
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
+}
+
+// MEMVUL_ATT_WAIT (default 5: r01n, 118 -> 111 us): how the attention kernel's single-lane TMA / MMA warps wait (bits 0-1 TMA warp, bits 2-3 MMA warp, bits 4-5
+// softmax warps; 0 spin, 1 suspend hint, 2 hint + nanosleep -- ptx.cuh mbar_wait_idle)
+static int att_wait_mode() {
+  static const int m = [] { const char* e = getenv("MEMVUL_ATT_WAIT"); return e ? atoi(e) & 63 : 5; }();
+  return m;
 }
 
 int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st,
@@ -354,7 +368,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt);
+      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }

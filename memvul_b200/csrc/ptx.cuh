@@ -58,6 +58,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware may park the thread for up to `ns` nanoseconds (it is released as
+// soon as the phase completes), so a single-lane role warp that waits for a long time does not burn the issue
+// slots of the compute warps sharing its scheduler with a tight SYNCS/BRA loop.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
+// idle = 0: plain wait; 1: suspend hint; 2: suspend hint + nanosleep back-off between polls
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, int idle) {
+  if (idle == 0) { mbar_wait(bar, parity); return; }
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if (idle == 2) __nanosleep(64);
+    if (++polls == (1u << 22)) {          // > 4 s of parked polling: certainly a deadlock
+      printf("memvul_b200: mbarrier deadlock (idle wait) block=%d thread=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if MV_DEADLOCK_TRAP
   long long t0 = 0;

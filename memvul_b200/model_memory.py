@@ -83,7 +83,10 @@ class ModelMemory(Model):
                  use_header: bool = True,
                  temperature: float = 1,
                  initializer=None,
-                 regularizer=None) -> None:
+                 regularizer=None,
+                 *, header_dim: int = 512) -> None:
+        # header_dim: the reference hard-codes 512 (model_memory.py:70); keyword-only so that toy-sized test models can
+        # shrink it without touching the reference's positional / config signature
         super().__init__(vocab, regularizer)
         self.device = torch.device(device)
         self._use_header = use_header
@@ -96,7 +99,7 @@ class ModelMemory(Model):
         self._bert_pooler = BertPoolerWeights(embedding_dim)
         self._num_class = self.vocab.get_vocab_size(self._label_namespace)
         if use_header:
-            self._projector_single = FeedForwardWeights(embedding_dim, 512 if embedding_dim >= 512 else embedding_dim // 2)
+            self._projector_single = FeedForwardWeights(embedding_dim, header_dim)
             embedding_dim = self._projector_single.get_output_dim()
         self._projector = nn.Linear(3 * embedding_dim, 2, bias=False)
         self._temperature = temperature

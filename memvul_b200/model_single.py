@@ -32,7 +32,8 @@ class ModelSingle(Model):
                  label_namespace: str = "class_labels",
                  device: str = "cpu",
                  initializer=None,
-                 regularizer=None) -> None:
+                 regularizer=None,
+                 *, header_dim: int = 512) -> None:           # 512 in the reference (model_single.py:63); see ModelMemory
         super().__init__(vocab)
         self._device = torch.device(device)
         self._label_namespace = label_namespace
@@ -45,7 +46,7 @@ class ModelSingle(Model):
         self._num_class = self.vocab.get_vocab_size(self._label_namespace)
         if self._num_class != 2:
             raise NotImplementedError("memvul_b200's single head kernel is binary (pos/neg), as in the reference data")
-        header = 512 if dim >= 512 else dim // 2
+        header = header_dim
         self._projector = nn.Sequential(FeedForwardWeights(dim, header), nn.Linear(header, self._num_class, bias=False))
         self._metrics = {
             "accuracy": CategoricalAccuracy(),

@@ -34,6 +34,8 @@ class BertShape:
 BERT_BASE = BertShape()
 BERT_TINY = BertShape(vocab_size=1024, hidden=128, layers=2, heads=2, intermediate=512,
                       max_pos=512, header=64)
+# the same toy encoder under the reference's fixed 512-wide header: what a config-built model (from_params) has
+BERT_TINY_H512 = BertShape(vocab_size=1024, hidden=128, layers=2, heads=2, intermediate=512, max_pos=512, header=512)
 
 
 def synthetic_state_dict(shape: BertShape = BERT_BASE, seed: int = 2021,
@@ -142,7 +144,7 @@ def build_memory_model(shape: "BertShape" = None, seed: int = 2021, same_first: 
     shape = shape or BERT_BASE
     vocab = Vocabulary({"labels": ["same", "diff"] if same_first else ["diff", "same"]})
     emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape))
-    model = ModelMemory(vocab, BasicTextFieldEmbedder({"tokens": emb}), device=str(device or "cpu"))
+    model = ModelMemory(vocab, BasicTextFieldEmbedder({"tokens": emb}), device=str(device or "cpu"), header_dim=shape.header)
     sd = synthetic_state_dict(shape, seed)
     load_into(model, sd)
     model.eval()

@@ -14,7 +14,7 @@ from memvul_b200 import predict_memory as PM
 from memvul_b200.collate import batches, collate_instances
 from memvul_b200.custom_metric import SiameseMeasureV1, confusion, find_best_thres
 from memvul_b200.registrable import DatasetReader, Metric, Model, TokenEmbedder, Vocabulary
-from memvul_b200.synthetic import BERT_TINY, build_memory_model, synthetic_state_dict
+from memvul_b200.synthetic import BERT_TINY, BERT_TINY_H512, build_memory_model, synthetic_state_dict
 from memvul_b200.tokenizer import WordPieceTokenizer
 
 from toy_vocab import TOY_VOCAB  # noqa: E402
@@ -41,9 +41,14 @@ def test_registered_names_match_reference():
 def test_constructor_keywords_match_reference():
     want_model = ["vocab", "text_field_embedder", "PTM", "dropout", "label_namespace", "device", "use_header",
                   "temperature", "initializer", "regularizer"]                     # model_memory.py:41-51
-    assert list(inspect.signature(memvul_b200.ModelMemory.__init__).parameters)[1:] == want_model
+    sig = inspect.signature(memvul_b200.ModelMemory.__init__).parameters
+    assert list(sig)[1:len(want_model) + 1] == want_model
+    # additions are keyword-only and default to the reference's behaviour (header width 512, model_memory.py:70)
+    assert all(p.kind is p.KEYWORD_ONLY for p in list(sig.values())[len(want_model) + 1:]) and sig["header_dim"].default == 512
     want_single = ["vocab", "text_field_embedder", "PTM", "dropout", "label_namespace", "device", "initializer", "regularizer"]
-    assert list(inspect.signature(memvul_b200.ModelSingle.__init__).parameters)[1:] == want_single   # model_single.py:38-46
+    sig = inspect.signature(memvul_b200.ModelSingle.__init__).parameters
+    assert list(sig)[1:len(want_single) + 1] == want_single                          # model_single.py:38-46
+    assert all(p.kind is p.KEYWORD_ONLY for p in list(sig.values())[len(want_single) + 1:]) and sig["header_dim"].default == 512
     want_emb = ["model_name", "max_length", "sub_module", "train_parameters", "eval_mode", "last_layer_only",
                 "override_weights_file", "override_weights_strip_prefix", "gradient_checkpointing", "tokenizer_kwargs",
                 "transformer_kwargs", "pretrained_model_path"]                       # custom_PTM_embedder.py:66-81
@@ -224,7 +229,7 @@ def test_human_readable_schema_and_cal_metrics(tmp_path):
 
 def test_load_archive_roundtrip(tmp_path, vocab_file):
     """predict_memory.py:62-67: config.json + vocabulary/ + weights.th, with dict overrides."""
-    model, sd = build_memory_model(BERT_TINY)
+    model, sd = build_memory_model(BERT_TINY_H512)             # a config-built model has the reference's 512-wide header
     d = tmp_path / "ser"
     (d / "vocabulary").mkdir(parents=True)
     (d / "vocabulary" / "labels.txt").write_text("diff\nsame\n")

@@ -184,7 +184,7 @@ def test_model_single_matches_oracle():
     from oracle import memvul_oracle as O
     sd = synthetic_state_dict(BERT_TINY, model="single")
     emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(BERT_TINY))
-    model = ModelSingle(Vocabulary({"class_labels": ["neg", "pos"]}), BasicTextFieldEmbedder({"tokens": emb}))
+    model = ModelSingle(Vocabulary({"class_labels": ["neg", "pos"]}), BasicTextFieldEmbedder({"tokens": emb}), header_dim=BERT_TINY.header)
     load_into(model, sd)
     model.eval().cuda()
     ids, mask, tids = synthetic_ids(4, 128, lens=[128, 9, 64, 100], vocab_size=1024)   # config C1 shape: B=4, S=128
@@ -203,7 +203,7 @@ def test_predict_driver_end_to_end(tmp_path_factory):
     """predict_memory.test_siamese flow on a toy archive: archive -> bank (128+rest) -> batches -> JSON lines -> cal_metrics."""
     import tarfile
     from memvul_b200 import predict_memory as PM
-    from memvul_b200.synthetic import BERT_TINY, synthetic_state_dict
+    from memvul_b200.synthetic import BERT_TINY_H512, synthetic_state_dict
     from toy_vocab import TOY_VOCAB
     d = tmp_path_factory.mktemp("arch")
     vocab_file = d / "vocab.txt"
@@ -221,7 +221,7 @@ def test_predict_driver_end_to_end(tmp_path_factory):
                                       "num_attention_heads": 2, "intermediate_size": 512}}}}},
            "validation_data_loader": {"batch_size": 4, "shuffle": False}}
     (d / "config.json").write_text(json.dumps(cfg))
-    torch.save(synthetic_state_dict(BERT_TINY), d / "weights.th")
+    torch.save(synthetic_state_dict(BERT_TINY_H512), d / "weights.th")
     with tarfile.open(d / "model.tar.gz", "w:gz") as t:
         for n in ("config.json", "weights.th", "vocabulary"):
             t.add(d / n, arcname=n)
@@ -385,7 +385,7 @@ def test_model_single_matches_the_reference_run(name):
         j = json.load(f)
     shape = BertShape(**j["shape"])
     emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape))
-    model = ModelSingle(Vocabulary({"class_labels": j["label_vocab"]}), BasicTextFieldEmbedder({"tokens": emb}))
+    model = ModelSingle(Vocabulary({"class_labels": j["label_vocab"]}), BasicTextFieldEmbedder({"tokens": emb}), header_dim=shape.header)
     load_into(model, synthetic_state_dict(shape, model="single"))
     model.eval().cuda()
     with torch.no_grad():
