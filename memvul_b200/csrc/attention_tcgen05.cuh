@@ -104,7 +104,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
 
   if (warp_idx == 5) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // The whole warp walks the schedule (uniform control flow keeps the address arithmetic on the uniform datapath);
+    // one elected lane issues.  Under `if (lane == 0)` ptxas wrapped every TMA / MMA instruction in an
+    // ELECT / R2UR / BRA.U.ANY waterfall (~16 SASS instructions per tcgen05.mma).
+    {
+      const bool issuer = elect_one();
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, h, q0, len;
@@ -113,23 +117,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         const int nkb = (len + C::BKV - 1) / C::BKV;
         const int row_base = b * S;
         mbar_wait_idle(q_empty, (it & 1u) ^ 1u, idle_tma);     // previous item's last Q K^T has retired
-        mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-        tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_base + q0, kEvictFirst);
+        if (issuer) {
+          mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+          tma_load_2d(smem + C::OFF_Q, &tmap_qkv, q_full, h * C::DH, row_base + q0, kEvictFirst);
+        }
         for (int j = 0; j < nkb; ++j, ++g) {
           const uint32_t st = g % C::KV_STAGES;
           mbar_wait_idle(&kv_empty[st], ((g / C::KV_STAGES) & 1u) ^ 1u, idle_tma);
           const int row_k = row_base + j * C::BKV;
-          mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
-          tma_load_2d(smem + C::OFF_K + st * C::KV_BYTES, &tmap_kv, &k_full[st], H + h * C::DH, row_k, kEvictLast);
-          mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
-          tma_load_2d(smem + C::OFF_V + st * C::KV_BYTES, &tmap_kv, &v_full[st], 2 * H + h * C::DH, row_k, kEvictLast);
+          if (issuer) {
+            mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
+            tma_load_2d(smem + C::OFF_K + st * C::KV_BYTES, &tmap_kv, &k_full[st], H + h * C::DH, row_k, kEvictLast);
+            mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
+            tma_load_2d(smem + C::OFF_V + st * C::KV_BYTES, &tmap_kv, &v_full[st], 2 * H + h * C::DH, row_k, kEvictLast);
+          }
         }
         ++it;
       }
     }
   } else if (warp_idx == 4) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();
+      const uint32_t smem_base = smem_u32(smem);
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, C::BKV, false, false);   // S = Q K^T   (both K-major)
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);        // O += P V    (V is N-major)
       uint32_t g0 = 0, it = 0;                                  // g0 = global index of the item's first block
@@ -138,20 +148,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         decode(item, b, h, q0, len);
         if (q0 >= len) continue;
         const int nkb = (len + C::BKV - 1) / C::BKV;
-        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + C::OFF_Q));
+        const uint64_t q_desc = umma_desc_sw128(smem_base + C::OFF_Q);
         auto issue_qk = [&](int j) {
           const uint32_t g = g0 + static_cast<uint32_t>(j);
           const uint32_t st = g % C::KV_STAGES;
           mbar_wait_idle(&k_full[st], (g / C::KV_STAGES) & 1u, idle_mma);
           tc_fence_after();
-          const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + C::OFF_K + st * C::KV_BYTES));
+          const uint64_t k_desc = umma_desc_sw128(smem_base + C::OFF_K + st * C::KV_BYTES);
           const uint32_t d = tmem_base + C::TM_S + (g & 1u) * C::BKV;
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
-                        k != 0 ? 1u : 0u);
-          umma_commit(&s_full[g & 1u]);
-          if (j == nkb - 1) umma_commit(q_empty);              // Q may be overwritten once this product retires
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
+                          k != 0 ? 1u : 0u);
+            umma_commit(&s_full[g & 1u]);
+            if (j == nkb - 1) umma_commit(q_empty);            // Q may be overwritten once this product retires
+          }
         };
         mbar_wait_idle(q_full, it & 1u, idle_mma);
         // S[g&1] of the first two blocks is free: the previous item's last two p_full phases were waited on below.
@@ -164,18 +176,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           if (j == 0) mbar_wait_idle(o_free, (it & 1u) ^ 1u, idle_mma);   // previous item's O has been read out
           mbar_wait_idle(&v_full[st], (g / C::KV_STAGES) & 1u, idle_mma);
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + C::OFF_P + (g & 1u) * C::P_BYTES);
-          const uint32_t v_addr = smem_u32(smem + C::OFF_V + st * C::KV_BYTES);
+          const uint32_t p_addr = smem_base + C::OFF_P + (g & 1u) * C::P_BYTES;
+          const uint32_t v_addr = smem_base + C::OFF_V + st * C::KV_BYTES;
+          if (issuer) {
 #pragma unroll
-          for (int kk = 0; kk < C::BKV / 16; ++kk) {
-            // A = P: K-major 64-wide chunk, 32 B per K=16 step.  B = V: N-major (one 128 B swizzle row per key),
-            // 16 keys = 2048 B per step.
-            const uint64_t a_desc = umma_desc_sw128(p_addr) + static_cast<uint64_t>(kk * 2);
-            const uint64_t b_desc = umma_desc_sw128(v_addr + kk * 2048);
-            umma_f16_ss(tmem_base + C::TM_O, a_desc, b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < C::BKV / 16; ++kk) {
+              // A = P: K-major 64-wide chunk, 32 B per K=16 step.  B = V: N-major (one 128 B swizzle row per key),
+              // 16 keys = 2048 B per step.
+              const uint64_t a_desc = umma_desc_sw128(p_addr) + static_cast<uint64_t>(kk * 2);
+              const uint64_t b_desc = umma_desc_sw128(v_addr + kk * 2048);
+              umma_f16_ss(tmem_base + C::TM_O, a_desc, b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g & 1u]);
+            umma_commit(&kv_empty[st]);                        // K/V stage reusable once Q K_g^T and P_g V_g retired
           }
-          umma_commit(&pv_done[g & 1u]);
-          umma_commit(&kv_empty[st]);                          // K/V stage reusable once Q K_g^T and P_g V_g retired
           if (j + 2 < nkb) issue_qk(j + 2);                    // S[g&1] is free; runs under the softmax of block g+1
         }
         g0 += static_cast<uint32_t>(nkb);

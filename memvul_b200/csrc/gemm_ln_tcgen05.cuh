@@ -90,7 +90,9 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 
   if (warp_idx == 0) {
     // ===================== TMA producer (all CTAs) =====================
-    if (lane == 0) {
+    // warp-uniform loops, one elected lane issues (see gemm_tcgen05_2cta.cuh: avoids ptxas' per-instruction waterfall)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -98,6 +100,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&empty_bar[stage], phase ^ 1u, idle_tma);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          if (issuer) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           if (a_multicast) {
             // The three pairs need the SAME 128 A rows per rank: pairs 0 and 1 each fetch 64 of them once and the TMA
@@ -111,14 +114,17 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
             tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
           }
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (even rank of each pair) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, Cfg::BN, false, false);
+      const bool issuer = elect_one();
+      const uint32_t smem_base = smem_u32(smem);
       const uint16_t pair_mask = static_cast<uint16_t>(0b11u << (pair * 2));
       int stage = 0;
       uint32_t phase = 0;
@@ -131,17 +137,19 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&full_bar[stage], phase, idle_mma);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(sa);
           const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k)
-            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], a_multicast ? static_cast<uint16_t>(0b111111) : pair_mask);
+            for (int k = 0; k < Cfg::BK / 16; ++k)
+              umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], a_multicast ? static_cast<uint16_t>(0b111111) : pair_mask);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&tfull_bar[acc], pair_mask);
+        if (issuer) umma_commit_pair(&tfull_bar[acc], pair_mask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

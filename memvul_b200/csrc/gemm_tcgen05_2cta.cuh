@@ -100,7 +100,9 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
 
   if (warp_idx == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (same reason as the MMA warp below: no per-instruction waterfall)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -110,17 +112,25 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&empty_bar[stage], phase ^ 1u, idle_tma);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
-          tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
+          if (issuer) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictNormal);
+            tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // The whole warp walks the loop (uniform control flow, so the descriptor arithmetic stays on the uniform datapath)
+    // and one elected lane issues: with `if (lane == 0)` around everything ptxas wrapped EVERY tcgen05.mma in an
+    // ELECT / 5x R2UR / BRA.U.ANY waterfall (~16 SASS instructions per MMA, ~95 per K-block), and under the
+    // erf-GELU epilogue warps sharing this scheduler the issue thread fell behind the tensor pipe (r01n/r01o).
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, Cfg::BN, false, false);
+      const bool issuer = elect_one();
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -132,17 +142,19 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&full_bar[stage], phase, idle_mma);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(sa);
           const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k)
-            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], 0b11);       // frees the slot in both CTAs
+            for (int k = 0; k < Cfg::BK / 16; ++k)
+              umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 0b11);     // frees the slot in both CTAs
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&tfull_bar[acc], 0b11);           // accumulators of both CTAs are complete
+        if (issuer) umma_commit_pair(&tfull_bar[acc], 0b11);   // accumulators of both CTAs are complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
