@@ -137,3 +137,28 @@ class FBetaMeasure:
         if reset:
             self.reset()
         return out
+
+
+class ClassificationReport:
+    """The accuracy / weighted-F1 / per-class-F1 trio both models keep (model_memory.py:80-84, model_single.py:68-72) and
+    the flat dict their ``get_metrics`` report (model_memory.py:196-207): one place instead of two copies."""
+
+    def __init__(self, num_classes: int, idx2label: Dict[int, str]) -> None:
+        self.idx2label = idx2label
+        self.parts = {"accuracy": CategoricalAccuracy(),
+                      "f1-score_overall": FBetaMeasure(num_classes, average="weighted"),
+                      "f1-score_each": FBetaMeasure(num_classes, average=None)}
+
+    def update(self, predictions, gold_labels) -> None:
+        for m in self.parts.values():
+            m(predictions, gold_labels)
+
+    def report(self, reset: bool) -> Dict[str, float]:
+        out: Dict[str, float] = {"accuracy": self.parts["accuracy"].get_metric(reset)}
+        overall = self.parts["f1-score_overall"].get_metric(reset)
+        out.update({"precision": overall["precision"], "recall": overall["recall"], "f1-score": overall["fscore"]})
+        each = self.parts["f1-score_each"].get_metric(reset)
+        for i, name in sorted(self.idx2label.items()):
+            for short, key in (("precision", "precision"), ("recall", "recall"), ("f1-score", "fscore")):
+                out[f"{name}_{short}"] = each[key][i]
+        return out

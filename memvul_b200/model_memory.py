@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import native
-from .custom_metric import CategoricalAccuracy, FBetaMeasure, SiameseMeasureV1
+from .custom_metric import ClassificationReport, SiameseMeasureV1
 from .modules import BasicTextFieldEmbedder, BertPoolerWeights, FeedForwardWeights
 from .registrable import Model, TokenEmbedder, Vocabulary
 
@@ -108,11 +108,8 @@ class ModelMemory(Model):
         self._golden_instances_labels: Optional[List[str]] = None
         self._vterm = None            # (key, tensor) cache of Wv . bank
 
-        self._metrics = {
-            "accuracy": CategoricalAccuracy(),
-            "f1-score_overall": FBetaMeasure(self._num_class, average="weighted"),
-            "f1-score_each": FBetaMeasure(self._num_class, average=None),
-        }
+        self._report = ClassificationReport(self._num_class, self._idx2token_label)
+        self._metrics = self._report.parts                        # the reference's attribute name (model_memory.py:80)
         self._siamese_metric = SiameseMeasureV1(self._same_idx)
         self._pending: List[Dict[str, Any]] = []      # metric updates waiting for their device->host copy
         if initializer is not None:
@@ -240,8 +237,7 @@ class ModelMemory(Model):
             probs = e["best_probs"].numpy()
             if e["label"] is not None:
                 gold = e["label"].numpy()
-                for metric in self._metrics.values():
-                    metric(probs, gold)
+                self._report.update(probs, gold)
             self._siamese_metric(probs, e["metadata"])
 
     # ------------------------------------------------------------------ outputs
@@ -265,15 +261,7 @@ class ModelMemory(Model):
 
     def get_metrics(self, reset: bool = False) -> Dict[str, float]:
         self._flush_metrics()
-        metrics = dict()
-        metrics["accuracy"] = self._metrics["accuracy"].get_metric(reset)
-        precision, recall, fscore = self._metrics["f1-score_overall"].get_metric(reset).values()
-        metrics["precision"], metrics["recall"], metrics["f1-score"] = precision, recall, fscore
-        precision, recall, fscore = self._metrics["f1-score_each"].get_metric(reset).values()
-        for i in range(self._num_class):
-            metrics[f"{self._idx2token_label[i]}_precision"] = precision[i]
-            metrics[f"{self._idx2token_label[i]}_recall"] = recall[i]
-            metrics[f"{self._idx2token_label[i]}_f1-score"] = fscore[i]
+        metrics = self._report.report(reset)
         if reset:
             s = self._siamese_metric.get_metric(reset)
             metrics["s_precision"], metrics["s_recall"], metrics["s_f1-score"] = s["precision"], s["recall"], s["f1"]

@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from . import native
-from .custom_metric import CategoricalAccuracy, FBetaMeasure
+from .custom_metric import ClassificationReport
 from .model_memory import _tokens, build_text_field_embedder
 from .modules import BertPoolerWeights, FeedForwardWeights
 from .registrable import Model, Vocabulary
@@ -48,11 +48,8 @@ class ModelSingle(Model):
             raise NotImplementedError("memvul_b200's single head kernel is binary (pos/neg), as in the reference data")
         header = header_dim
         self._projector = nn.Sequential(FeedForwardWeights(dim, header), nn.Linear(header, self._num_class, bias=False))
-        self._metrics = {
-            "accuracy": CategoricalAccuracy(),
-            "f1-score_overall": FBetaMeasure(self._num_class, average="weighted"),
-            "f1-score_each": FBetaMeasure(self._num_class, average=None),
-        }
+        self._report = ClassificationReport(self._num_class, self._idx2token_label)
+        self._metrics = self._report.parts                        # the reference's attribute name (model_single.py:68)
         if initializer is not None:
             initializer(self)
 
@@ -81,8 +78,7 @@ class ModelSingle(Model):
             lg = logits.cpu().double()
             lse = torch.logsumexp(lg, dim=-1)
             output_dict["loss"] = (lse - lg[torch.arange(B), gold]).mean().float()
-            for metric in self._metrics.values():
-                metric(probs_h.numpy(), gold.numpy())
+            self._report.update(probs_h.numpy(), gold.numpy())
         return output_dict
 
     def make_output_human_readable(self, output_dict: Dict[str, Any]):
@@ -97,13 +93,4 @@ class ModelSingle(Model):
         return rows
 
     def get_metrics(self, reset: bool = False) -> Dict[str, float]:
-        metrics = dict()
-        metrics["accuracy"] = self._metrics["accuracy"].get_metric(reset)
-        precision, recall, fscore = self._metrics["f1-score_overall"].get_metric(reset).values()
-        metrics["precision"], metrics["recall"], metrics["f1-score"] = precision, recall, fscore
-        precision, recall, fscore = self._metrics["f1-score_each"].get_metric(reset).values()
-        for i in range(self._num_class):
-            metrics[f"{self._idx2token_label[i]}_precision"] = precision[i]
-            metrics[f"{self._idx2token_label[i]}_recall"] = recall[i]
-            metrics[f"{self._idx2token_label[i]}_f1-score"] = fscore[i]
-        return metrics
+        return self._report.report(reset)                         # model_single.py:112-124
