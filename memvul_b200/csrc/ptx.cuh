@@ -17,8 +17,6 @@ namespace mv {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -187,32 +185,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-// two exponentials per MUFU issue: {2^hi, 2^lo} in fp16 from two fp32 exponents (rounded to fp16 first)
-__device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
-  uint32_t h, r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
-  return r;
-}
-
-
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -344,8 +316,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's committed bulk groups have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // erf(x) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): 2 MUFU + ~10 FP32 ops instead of erff()'s ~25.
 // Used only where the result is rounded to fp16 afterwards (GELU epilogue), where 1.5e-7 is invisible.
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -394,8 +364,6 @@ __device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t (&v)[8])
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B, for a tile whose rows are 128 bytes
 // (64 fp16) and whose 8-row groups are 1024 bytes apart -- exactly what a TMA box of
@@ -425,11 +393,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, bool a_mn_ma
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
