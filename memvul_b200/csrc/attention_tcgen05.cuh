@@ -44,12 +44,18 @@ struct AttnCfg {
 
 __global__ void __launch_bounds__(AttnCfg::THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
-                         const int* __restrict__ lens, __half* __restrict__ ctx, int B, int S, int H, int n_qt, int wait_mode) {
+                         const int* __restrict__ lens, __half* __restrict__ ctx, int B, int S, int H, int n_qt, int wait_mode,
+                         unsigned long long* __restrict__ trace) {
   using C = AttnCfg;
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
   const int n_heads = H / C::DH;
   const int n_items = B * n_heads * n_qt;                  // n_qt = query tiles per sequence that are computed
+  // debug only (MEMVUL_ATT_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 128 key blocks
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](uint32_t g, int slot, int k) {
+    if (tracing && g < 128u) trace[slot * 1024 + g * 8 + k] = static_cast<unsigned long long>(clock64());
+  };
   const int idle_tma = wait_mode & 3, idle_mma = (wait_mode >> 2) & 3, idle_sm = (wait_mode >> 4) & 3;   // see mbar_wait_idle
 
   extern __shared__ __align__(1024) uint8_t smem[];        // SWIZZLE_128B tiles need 1024-byte alignment
@@ -173,9 +179,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           const uint32_t g = g0 + static_cast<uint32_t>(j);
           const uint32_t st = g % C::KV_STAGES;
           mbar_wait_idle(&p_full[g & 1u], (g >> 1) & 1u, idle_mma);   // P_g in smem, S[g&1] drained, O rescaled
+          if (issuer) stamp(g, 1, 0);
           if (j == 0) mbar_wait_idle(o_free, (it & 1u) ^ 1u, idle_mma);   // previous item's O has been read out
           mbar_wait_idle(&v_full[st], (g / C::KV_STAGES) & 1u, idle_mma);
           tc_fence_after();
+          if (issuer) stamp(g, 1, 1);
           const uint32_t p_addr = smem_base + C::OFF_P + (g & 1u) * C::P_BYTES;
           const uint32_t v_addr = smem_base + C::OFF_V + st * C::KV_BYTES;
           if (issuer) {
@@ -190,7 +198,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             umma_commit(&pv_done[g & 1u]);
             umma_commit(&kv_empty[st]);                        // K/V stage reusable once Q K_g^T and P_g V_g retired
           }
+          if (issuer) stamp(g, 1, 2);
           if (j + 2 < nkb) issue_qk(j + 2);                    // S[g&1] is free; runs under the softmax of block g+1
+          if (issuer) stamp(g, 1, 3);
         }
         g0 += static_cast<uint32_t>(nkb);
         ++it;
@@ -206,6 +216,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       int b, h, q0, len;
       decode(item, b, h, q0, len);
       const size_t row_base = static_cast<size_t>(b) * S;
+      if (warp_idx == 0 && lane == 0 && len >= 0) stamp(g, 1, 7);      // len forces the lens[b] load to have landed
       if (q0 >= len) {
         // fully padded query tile: deterministic zeros, no tensor work
         const int rows = min(C::BQ, S - q0);
@@ -218,13 +229,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       const int nkb = (len + C::BKV - 1) / C::BKV;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkb; ++j, ++g) {
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 0);
         mbar_wait_idle(&s_full[g & 1u], (g >> 1) & 1u, idle_sm);
         tc_fence_after();
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 1);
         uint32_t s[2][32];
         const uint32_t s_addr = tmem_base + lane_addr + C::TM_S + (g & 1u) * C::BKV;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) tmem_ld_32x32b_x32(s_addr + cc * 32, s[cc]);
         tmem_wait_ld();
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 2);
         const int valid = min(C::BKV, len - j * C::BKV);       // >= 1
         if (valid < C::BKV) {                                  // only the last key block of a sequence is ragged
 #pragma unroll
@@ -251,6 +265,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         const bool grow = (mx - m_run) * c > 8.0f;             // true on the first block (m_run = -inf)
         const bool any_grow = __any_sync(0xffffffffu, grow);
         const float m_new = grow ? mx : m_run;
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 3);
         const float mc = m_new * c;
         uint8_t* p_row = smem + C::OFF_P + (g & 1u) * C::P_BYTES + r * 128;   // P[g&1]: P V of block g-2 retired long ago
         float l4[4] = {0.f, 0.f, 0.f, 0.f};                   // independent partial sums (ILP)
@@ -276,6 +291,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           }
         }
         const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 4);
         const float alpha = ex2_approx((m_run - m_new) * c);   // 0 on the first block (m_run = -inf), else 1 unless grown
         if (j > 0) {
           mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);   // O holds blocks 0..j-1 of this item
@@ -294,16 +310,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             tmem_wait_st();
           }
         }
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 5);
         l_run = l_run * alpha + l_blk;
         m_run = m_new;
         fence_proxy_async_smem();        // P (generic-proxy stores) -> visible to the tensor core's async proxy
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1u]);
+        if (warp_idx == 0 && lane == 0) stamp(g, 0, 6);
       }
       // ---------------- O / l -> ctx ----------------
       mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);
       tc_fence_after();
+      if (warp_idx == 0 && lane == 0) stamp(g - 1, 0, 7);
       const float inv_l = 1.0f / l_run;
       const int q = q0 + r;
       __half* orow = ctx + (row_base + q) * H + h * C::DH;
@@ -311,9 +330,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       tmem_ld_32x32b_x32(tmem_base + lane_addr + C::TM_O, o[0]);
       tmem_ld_32x32b_x32(tmem_base + lane_addr + C::TM_O + 32, o[1]);
       tmem_wait_ld();
+      if (warp_idx == 0 && lane == 0) stamp(g - 1, 1, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);                      // the next item's first P V may overwrite O now
+      if (warp_idx == 0 && lane == 0) stamp(g - 1, 1, 5);
       if (q < S) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -328,6 +349,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           }
         }
       }
+      if (warp_idx == 0 && lane == 0) stamp(g - 1, 1, 6);
     }
   }
 

@@ -366,10 +366,23 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
   const int n_items = B * (H / 64) * n_qt;
   const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
+  // MEMVUL_ATT_TRACE=<file>: debug only -- CTA 0 records clock64() per soft-max / MMA phase (tools/att_trace.py)
+  static const char* trace_path = getenv("MEMVUL_ATT_TRACE");
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_path && !trace_buf) {
+    CUDA_TRY(cudaMalloc(&trace_buf, 2048 * 8));
+  }
+  if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 2048 * 8, st));
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
+      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
   CUDA_TRY(cudaGetLastError());
+  if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
+    std::vector<unsigned long long> host(2048);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(host.data(), trace_buf, 2048 * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, 2048, f); fclose(f); }
+  }
   return MEMVUL_OK;
 }
 
