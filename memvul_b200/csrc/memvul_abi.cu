@@ -354,9 +354,10 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tctx;
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, &tq)) return rc;
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, mv::AttnCfg::BKV, &tkv)) return rc;
+  if (int rc = make_map_f16(ctx, (uint64_t)B * S, (uint64_t)H, (uint64_t)H, 32, &tctx)) return rc;   // ctx write-out boxes
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(mv::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -375,7 +376,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 2048 * 8, st));
   LaunchScope ls(KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+      tq, tkv, tctx, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
   CUDA_TRY(cudaGetLastError());
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
     std::vector<unsigned long long> host(2048);
