@@ -323,8 +323,8 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
     if (n < 1) return fail(MEMVUL_E_CUDA, "fused GEMM+LayerNorm: no 6-CTA cluster fits on this device");
     max_clusters = n;
   }
-  // TMA multicast of A across the three pairs works but measured 2-4 % slower than unicast (L2 already de-duplicates the
-  // three requests), so it is opt-in: MEMVUL_LN_MULTICAST=1.
+  // TMA multicast of A across the three pairs works but measured 2-4 % slower than unicast (the main loop is not
+  // L2-bound: DESIGN.md section 3), so it is opt-in: MEMVUL_LN_MULTICAST=1.
   static const bool a_mc = [] { const char* e = getenv("MEMVUL_LN_MULTICAST"); return e && strcmp(e, "1") == 0; }();
   CUtensorMap ta, ta64, tb, tres, t32, t16;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
