@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MEMVUL_ABI_VERSION 1
+#define MEMVUL_ABI_VERSION 2
 
 enum {
   MEMVUL_OK = 0,
@@ -35,7 +35,10 @@ enum {
 };
 
 /* memvul_encoder_forward flags */
-enum { MEMVUL_ENC_CLS_ONLY = 1 };
+enum {
+  MEMVUL_ENC_CLS_ONLY = 1,  /* only the [CLS] row of every sequence is the last layer's output          */
+  MEMVUL_ENC_PACKED = 2     /* token-major var-len execution: padded tokens are never computed (needs row_start) */
+};
 
 /* GEMM epilogues (memvul_gemm_f16) */
 enum {
@@ -71,25 +74,38 @@ typedef struct memvul_bert_weights {
 int memvul_abi_version(void);
 const char* memvul_last_error(void);
 
-/* Bytes of scratch memvul_encoder_forward needs for B sequences padded to S tokens. */
-size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S);
+/* Bytes of scratch memvul_encoder_forward needs for B sequences padded to S tokens with these flags.  With
+ * MEMVUL_ENC_PACKED the workspace must be zero-initialised once before its first use (afterwards it only ever holds
+ * finite values this library wrote), because rows past the last token of a partially filled tile are read. */
+size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S, int flags);
 
 /* Replaces PretrainedTransformerEmbedder.forward / HF BertModel.forward
  * (custom_PTM_embedder.py:224-235).
  *   token_ids [B,S] int64; type_ids [B,S] int64 or NULL (all zero, custom_PTM_embedder.py:199-202);
  *   lens [B] int32 = number of unmasked (prefix) tokens per sequence, 1 <= len <= S;
- *   hidden_out [B*S, H] fp32 = last_hidden_state (rows of padded tokens are unspecified).
+ *   row_start [B+1] int32 = exclusive prefix sum of lens (memvul_mask_to_lens fills it), or NULL without
+ *     MEMVUL_ENC_PACKED;
+ *   hidden_out [B*S, H] fp32 = last_hidden_state in the PADDED layout (row b*S + s); rows of padded tokens are
+ *     zero with MEMVUL_ENC_PACKED and unspecified-but-finite without it;
+ *   bad_flag: device int32 (or NULL), bit 1 is set when a token id / type id was out of range (the reference's
+ *     torch.embedding raises; custom_PTM_embedder.py:205 raises for type ids) -- the host reads it with its results.
  * flags: MEMVUL_ENC_CLS_ONLY -- only hidden_out[b*S + 0] (the [CLS] row BertPooler reads, model_memory.py:99) is the
  *   last layer's output; the last layer then runs its attention on the first query tile and its output projection /
  *   FFN / LayerNorms on B rows instead of B*S (identical arithmetic per row; ~1/12 of the encoder's work saved).
+ *   MEMVUL_ENC_PACKED -- the reference pads every batch to its longest member (config_memory.json:50-57) and pays
+ *   for the padding in every GEMM; here the embedding kernel writes the valid tokens of all sequences back to back
+ *   (token-major, sequence b at rows row_start[b]..row_start[b+1]) and every kernel reads the row count from
+ *   row_start[B] ON THE DEVICE, so no host synchronisation is needed and padded tokens cost nothing.
  * Supported: H in {128, 768} (H % 128 == 0, head_dim == 64), S <= 512, S <= max_pos. */
 int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
-                           const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
-                           size_t workspace_bytes, int flags, void* stream);
+                           const int32_t* lens, const int32_t* row_start, int B, int S, float* hidden_out,
+                           void* workspace, size_t workspace_bytes, int flags, int32_t* bad_flag, void* stream);
 
-/* bool mask [B,S] (1 byte each, AllenNLP `mask`) -> lens[B]; *bad_flag (device int32) is set to 1 if a
- * mask is not a non-empty prefix mask.  (custom_PTM_embedder.py:215-216 consumes the mask.) */
-int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* bad_flag, void* stream);
+/* bool mask [B,S] (1 byte each, AllenNLP `mask`) -> lens[B] and (if non-NULL) row_start[B+1] = exclusive prefix sum;
+ * *bad_flag (device int32) gets bit 0 set if a mask is not a non-empty prefix mask.
+ * (custom_PTM_embedder.py:215-216 consumes the mask.) */
+int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* row_start, int32_t* bad_flag,
+                        void* stream);
 
 /* Anchor-bank side term: vterm[g,c] = Wv[c] . bank[g]  (the v third of Linear(1536->2),
  * model_memory.py:141), computed once per bank build (model_memory.py:105-115). */
@@ -119,20 +135,26 @@ int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float
  * row statistics through distributed shared memory); N must be 768, M >= 256.  In place (x32 == resid) is allowed. */
 int memvul_gemm_ln_f16(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
                        const float* beta, float eps, float* x32, void* x16, int M, int N, int K, void* stream);
-/* ctx[B*S,H] fp16 = softmax(QK^T/8 + mask)V per head from qkv [B*S,3H] fp16; head_dim 64, S <= 512. */
-int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream);
+/* ctx[B*S,H] fp16 = softmax(QK^T/8 + mask)V per head from qkv [B*S,3H] fp16; head_dim 64, S <= 512.
+ * row_start NULL: padded layout (sequence b at rows b*S..); else packed layout (rows row_start[b]..+lens[b]). */
+int memvul_attention_f16(const void* qkv, const int32_t* lens, const int32_t* row_start, void* ctx, int B, int S,
+                         int H, void* stream);
 /* x32/x16 = LayerNorm(y) rows; x32 or x16 may be NULL; in-place x32 == y allowed. */
 int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16,
                      int M, int H, void* stream);
-/* K1: LayerNorm(word[ids] + pos + type) -> x32, x16. */
-int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids, int B,
-                           int S, float* x32, void* x16, void* stream);
+/* K1: LayerNorm(word[ids] + pos + type) -> x32, x16 (token ids are always the padded [B,S] matrix).  row_start NULL:
+ * padded output rows b*S+s; else packed output rows row_start[b]+s for s < lens[b].  bad_flag (nullable): bit 1 is
+ * set on an out-of-range token / type id. */
+int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
+                           const int32_t* lens, const int32_t* row_start, int B, int S, float* x32, void* x16,
+                           int32_t* bad_flag, void* stream);
 
 /* ---- measurement hooks (bench.py) ----
  * Kernel classes, in the order memvul_profile_read fills them:
  *   0 embed_ln, 1 gemm_qkv, 2 attention, 3 gemm_attn_out, 4 layernorm, 5 gemm_ffn_up, 6 gemm_ffn_down,
- *   7 pool_match, 8 other. */
-#define MEMVUL_KERNEL_CLASSES 9
+ *   7 pool_match, 8 other, 9 attention_cls (first query tile of the CLS-only last layer), 10 cls_tail (the B-row
+ *   GEMMs / LayerNorms of the CLS-only last layer). */
+#define MEMVUL_KERNEL_CLASSES 11
 /* Number of kernels this library has launched in the calling process (all threads). */
 long long memvul_launch_count(void);
 /* When enabled, every launch is bracketed by CUDA events on its stream (adds ~2 us per launch). */

@@ -45,7 +45,8 @@ struct AttnCfg {
 __global__ void __launch_bounds__(AttnCfg::THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
                          const __grid_constant__ CUtensorMap tmap_ctx,
-                         const int* __restrict__ lens, __half* __restrict__ ctx, int B, int S, int H, int n_qt, int wait_mode,
+                         const int* __restrict__ lens, const int* __restrict__ row_start, __half* __restrict__ ctx,
+                         int B, int S, int H, int n_qt, int wait_mode,
                          unsigned long long* __restrict__ trace) {
   using C = AttnCfg;
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -102,12 +103,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   const uint32_t tmem_base = *tmem_slot;
 
   // Every role walks the same item sequence; `g` counts key blocks and `it` non-skipped items over the CTA's life.
-  auto decode = [&](int item, int& b, int& h, int& q0, int& len) {
+  // Token-major row of sequence b's first token: b*S in the padded layout, row_start[b] in the packed (var-len) one.
+  auto decode = [&](int item, int& b, int& h, int& q0, int& len, int& row_base) {
     const int qt = item % n_qt;
     h = (item / n_qt) % n_heads;
     b = item / (n_qt * n_heads);
     q0 = qt * C::BQ;
     len = lens[b];
+    row_base = row_start ? row_start[b] : b * S;
   };
 
   if (warp_idx == 5) {
@@ -119,11 +122,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       const bool issuer = elect_one();
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int b, h, q0, len;
-        decode(item, b, h, q0, len);
+        int b, h, q0, len, row_base;
+        decode(item, b, h, q0, len, row_base);
         if (q0 >= len) continue;
         const int nkb = (len + C::BKV - 1) / C::BKV;
-        const int row_base = b * S;
         mbar_wait_idle(q_empty, (it & 1u) ^ 1u, idle_tma);     // previous item's last Q K^T has retired
         if (issuer) {
           mbar_arrive_expect_tx(q_full, C::Q_BYTES);
@@ -152,8 +154,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, false, true);        // O += P V    (V is N-major)
       uint32_t g0 = 0, it = 0;                                  // g0 = global index of the item's first block
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int b, h, q0, len;
-        decode(item, b, h, q0, len);
+        int b, h, q0, len, row_base;
+        decode(item, b, h, q0, len, row_base);
         if (q0 >= len) continue;
         const int nkb = (len + C::BKV - 1) / C::BKV;
         const uint64_t q_desc = umma_desc_sw128(smem_base + C::OFF_Q);
@@ -217,19 +219,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     bool store_pending = false;                                // this warp has a ctx TMA store reading its P rows
     // lens[] of the NEXT item is loaded one item ahead: the dependent global load (~650 cycles in the r01p trace) sat
     // on the serial path between two items
-    int len_next = (static_cast<int>(blockIdx.x) < n_items) ? lens[blockIdx.x / (n_qt * n_heads)] : 0;
+    int len_next = 0, rb_next = 0;
+    if (static_cast<int>(blockIdx.x) < n_items) {
+      const int b0 = blockIdx.x / (n_qt * n_heads);
+      len_next = lens[b0];
+      rb_next = row_start ? row_start[b0] : b0 * S;
+    }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qt = item % n_qt;
       const int h = (item / n_qt) % n_heads;
       const int b = item / (n_qt * n_heads);
       const int q0 = qt * C::BQ;
       const int len = len_next;
-      if (item + static_cast<int>(gridDim.x) < n_items) len_next = lens[(item + gridDim.x) / (n_qt * n_heads)];
-      const size_t row_base = static_cast<size_t>(b) * S;
+      const size_t row_base = static_cast<size_t>(rb_next);
+      if (item + static_cast<int>(gridDim.x) < n_items) {
+        const int bn = (item + gridDim.x) / (n_qt * n_heads);
+        len_next = lens[bn];
+        rb_next = row_start ? row_start[bn] : bn * S;
+      }
+      // rows of this sequence that exist in the token-major matrix: S (padded layout, padded rows are written too so
+      // that they stay finite) or len (packed layout: the next row already belongs to the next sequence)
+      const int row_limit = row_start ? len : S;
       if (warp_idx == 0 && lane == 0 && len >= 0) stamp(g, 1, 7);
       if (q0 >= len) {
-        // fully padded query tile: deterministic zeros, no tensor work
-        const int rows = min(C::BQ, S - q0);
+        // fully padded query tile: deterministic zeros, no tensor work (the packed layout has no such rows)
+        const int rows = row_start ? 0 : min(C::BQ, S - q0);
         for (int i = threadIdx.x; i < rows * 8; i += 128) {
           const int rr = i >> 3, u = i & 7;
           *reinterpret_cast<uint4*>(ctx + (row_base + q0 + rr) * H + h * C::DH + u * 8) = make_uint4(0, 0, 0, 0);
@@ -350,7 +364,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);                      // the next item's first P V may overwrite O now
       if (warp_idx == 0 && lane == 0) stamp(g - 1, 1, 5);
-      if (q0 + C::BQ <= S) {
+      if (q0 + C::BQ <= row_limit) {
         // Full tile: stage the warp's 32 rows in its quarter of the P buffer the item's last block used (its P V has
         // retired) and let the TMA engine write them.  The per-lane version -- every lane storing 8 x 16 B into its own
         // row, 1,536 B apart -- kept the warp ~1,900 cycles in the LSU at every item boundary (r01p trace).
@@ -375,7 +389,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
           bulk_commit_group();
         }
         store_pending = true;
-      } else if (q < S) {                                      // ragged last tile: rows >= S belong to the next sequence
+      } else if (q < row_limit) {                              // ragged last tile: later rows belong to the next sequence
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll

@@ -40,8 +40,10 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                            const __grid_constant__ CUtensorMap tmap_b,
                            const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x32,
                            const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast) {
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast,
+                           const int* __restrict__ m_dev) {
   using Cfg = GemmLnCfg;
+  if (m_dev) M = min(M, __ldg(m_dev));     // packed (var-len) batches: the row count lives on the device
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;

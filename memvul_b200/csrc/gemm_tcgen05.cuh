@@ -43,8 +43,9 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         int M, int N, int K, const float* __restrict__ bias, const float* resid, void* out,
-                        int ldo) {
+                        int ldo, const int* __restrict__ m_dev) {
   using Cfg = GemmCfg<BN>;
+  if (m_dev) M = min(M, __ldg(m_dev));     // packed (var-len) batches: the row count lives on the device
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);

@@ -46,8 +46,10 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                             int M, int N, int K, const float* __restrict__ bias, int store, void* out_ptr) {
+                             int M, int N, int K, const float* __restrict__ bias, int store, void* out_ptr,
+                             const int* __restrict__ m_dev) {
   using Cfg = Gemm2Cfg<EPI>;
+  if (m_dev) M = min(M, __ldg(m_dev));     // packed (var-len) batches: the row count lives on the device
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;

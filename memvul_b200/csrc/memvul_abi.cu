@@ -44,8 +44,9 @@ int fail(int code, const char* fmt, ...) {
 // CUDA events on the launching stream so bench.py can report per-kernel durations from the live run.
 enum KernelClass : int {
   KC_EMBED_LN = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_ATTN_OUT, KC_LAYERNORM, KC_GEMM_FFN_UP, KC_GEMM_FFN_DOWN,
-  KC_POOL_MATCH, KC_OTHER, KC_COUNT
+  KC_POOL_MATCH, KC_OTHER, KC_ATTENTION_CLS, KC_CLS_TAIL, KC_COUNT
 };
+static_assert(KC_COUNT == MEMVUL_KERNEL_CLASSES, "include/memvul_b200.h lists the kernel classes");
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_prof_on{0};
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
@@ -105,6 +106,32 @@ int device_info(DeviceInfo* out) {
   }
   *out = it->second;
   return MEMVUL_OK;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (device, function): cache per device, not per process
+// (a second device in the same process would otherwise launch the > 48 KB kernels without the opt-in).
+int ensure_dyn_smem(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> done;          // (device << 48 | function address) -> bytes set
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const uint64_t key = (static_cast<uint64_t>(dev) << 48) ^ static_cast<uint64_t>(reinterpret_cast<uintptr_t>(kern));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return MEMVUL_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+  return MEMVUL_OK;
+}
+// small per-device integer cache (occupancy results)
+int* per_device_slot(int which) {
+  static std::mutex mu;
+  static std::unordered_map<int, int> slots;              // key = device * 16 + which; value 0 = not computed yet
+  static int dummy = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return &dummy;
+  std::lock_guard<std::mutex> lk(mu);
+  return &slots[dev * 16 + which];                         // references into unordered_map stay valid across inserts
 }
 
 // ------------------------------------------------------------------ TMA tensor maps
@@ -188,29 +215,25 @@ int make_map_f16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, ui
 // ------------------------------------------------------------------ launchers
 template <int BN, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
-                const float* resid, void* out, int sms, cudaStream_t st) {
+                const float* resid, void* out, int sms, cudaStream_t st, const int* m_dev) {
   using Cfg = mv::GemmCfg<BN>;
   auto kern = mv::gemm_f16_tcgen05_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
   LaunchScope ls(g_cls, st);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, bias, resid, out, N);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, bias, resid, out, N, m_dev);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
 
 template <int BN>
 int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
-                    const float* resid, void* out, int sms, cudaStream_t st) {
+                    const float* resid, void* out, int sms, cudaStream_t st, const int* m_dev) {
   switch (epi) {
-    case MEMVUL_EPI_BIAS_F16: return launch_gemm<BN, mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
-    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm<BN, mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
-    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm<BN, mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_F16: return launch_gemm<BN, mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm<BN, mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm<BN, mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
   }
   return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -231,14 +254,10 @@ static int epi_mode() {
 
 template <int EPI>
 int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
-                     const float* resid, void* out, int sms, cudaStream_t st) {
+                     const float* resid, void* out, int sms, cudaStream_t st, const int* m_dev) {
   using Cfg = mv::Gemm2Cfg<EPI>;
   auto kern = mv::gemm_f16_tcgen05_2cta_kernel<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   static const bool nostore = getenv("MEMVUL_GEMM_NOSTORE") != nullptr;      // experiment: time the main loop alone
   static const bool direct_st = getenv("MEMVUL_GEMM_DIRECT_ST") != nullptr;   // experiment: 256-bit per-lane stores
   CUtensorMap tout, tres;
@@ -254,23 +273,25 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   if (tiles < clusters) clusters = tiles;
   LaunchScope ls(g_cls, st);
   kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias,
-                                                              (nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode())) | (gemm_wait_mode() << 8), out);   // __cluster_dims__(2,1,1)
+                                                              (nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode())) | (gemm_wait_mode() << 8), out, m_dev);   // __cluster_dims__(2,1,1)
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
 
 int launch_gemm_2cta_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const float* bias,
-                         const float* resid, void* out, int sms, cudaStream_t st) {
+                         const float* resid, void* out, int sms, cudaStream_t st, const int* m_dev) {
   switch (epi) {
-    case MEMVUL_EPI_BIAS_F16: return launch_gemm_2cta<mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
-    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm_2cta<mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st);
-    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm_2cta<mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st);
+    case MEMVUL_EPI_BIAS_F16: return launch_gemm_2cta<mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm_2cta<mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm_2cta<mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
   }
   return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
+// m_dev (nullable): device int holding the actual row count (<= M) of a packed batch; M is then the upper bound the
+// TMA maps and the launch grid are sized for.
 int gemm_impl(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
-              int epi, cudaStream_t st) {
+              int epi, cudaStream_t st, const int* m_dev = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(MEMVUL_E_INVALID, "GEMM with empty shape M=%d N=%d K=%d", M, N, K);
   if (K % 64 != 0 || N % 128 != 0)
     return fail(MEMVUL_E_INVALID, "GEMM needs K %% 64 == 0 and N %% 128 == 0 (M=%d N=%d K=%d)", M, N, K);
@@ -285,31 +306,32 @@ int gemm_impl(const void* a, const void* w, const float* bias, const float* resi
     CUtensorMap ta2, tb2;
     if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta2)) return rc;
     if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, &tb2)) return rc;
-    return launch_gemm_2cta_epi(epi, ta2, tb2, M, N, K, bias, resid, out, di.sms, st);
+    return launch_gemm_2cta_epi(epi, ta2, tb2, M, N, K, bias, resid, out, di.sms, st, m_dev);
   }
   const bool bn256 = (N % 256 == 0) && (tiles_m * (N / 256) >= di.sms);
   const int BN = bn256 ? 256 : 128;
   CUtensorMap ta, tb;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
   if (int rc = make_map_f16(w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN, &tb)) return rc;
-  return bn256 ? launch_gemm_epi<256>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st)
-               : launch_gemm_epi<128>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st);
+  return bn256 ? launch_gemm_epi<256>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st, m_dev)
+               : launch_gemm_epi<128>(epi, ta, tb, M, N, K, bias, resid, out, di.sms, st, m_dev);
 }
 
 
 // Fused residual GEMM + LayerNorm (N == 768): x32/x16 = LN(A W^T + bias + resid).  Falls back to the caller's
 // two-kernel path (returns 1) when the shape does not qualify.
 int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
-                 const float* beta, float eps, float* x32, void* x16, int M, int N, int K, cudaStream_t st) {
+                 const float* beta, float eps, float* x32, void* x16, int M, int N, int K, cudaStream_t st,
+                 const int* m_dev = nullptr) {
   using Cfg = mv::GemmLnCfg;
   static const bool disabled = [] { const char* e = getenv("MEMVUL_FUSED_LN"); return e && strcmp(e, "0") == 0; }();
   if (disabled || N != Cfg::N || K % 64 != 0 || M < Cfg::BM) return 1;
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   auto kern = mv::gemm_ln_f16_tcgen05_kernel;
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
+  int& max_clusters = *per_device_slot(0);
+  if (max_clusters <= 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(Cfg::CLUSTER * (di.sms / Cfg::CLUSTER));
     cfg.blockDim = dim3(Cfg::THREADS);
@@ -336,7 +358,7 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   const int tiles = (M + Cfg::BM - 1) / Cfg::BM;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   LaunchScope ls(g_cls, st);
-  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (gemm_wait_mode() << 4));
+  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (gemm_wait_mode() << 4), m_dev);
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
@@ -348,8 +370,8 @@ static int att_wait_mode() {
   return m;
 }
 
-int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, cudaStream_t st,
-                   bool first_tile_only = false) {
+int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_start, void* ctx, int B, int S, int H,
+                   cudaStream_t st, bool first_tile_only = false) {
   if (B <= 0 || S <= 0 || S > 512) return fail(MEMVUL_E_INVALID, "attention needs 1 <= S <= 512 (B=%d S=%d)", B, S);
   if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
   DeviceInfo di;
@@ -358,12 +380,7 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, &tq)) return rc;
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, mv::AttnCfg::BKV, &tkv)) return rc;
   if (int rc = make_map_f16(ctx, (uint64_t)B * S, (uint64_t)H, (uint64_t)H, 32, &tctx)) return rc;   // ctx write-out boxes
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(mv::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mv::AttnCfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc;
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
   const int n_items = B * (H / 64) * n_qt;
   const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
@@ -374,9 +391,9 @@ int attention_impl(const void* qkv, const int32_t* lens, void* ctx, int B, int S
     CUDA_TRY(cudaMalloc(&trace_buf, 2048 * 8));
   }
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 2048 * 8, st));
-  LaunchScope ls(KC_ATTENTION, st);
+  LaunchScope ls(first_tile_only ? KC_ATTENTION_CLS : KC_ATTENTION, st);
   mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, tctx, lens, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+      tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
   CUDA_TRY(cudaGetLastError());
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
     std::vector<unsigned long long> host(2048);
@@ -392,7 +409,7 @@ int layernorm_impl(const float* y, const float* g, const float* b, float eps, fl
   if (M <= 0) return fail(MEMVUL_E_INVALID, "layernorm with M=%d", M);
   if (x32_stride == 0) x32_stride = H;
   const int blocks = (M + 7) / 8;
-  LaunchScope ls(KC_LAYERNORM, st);
+  LaunchScope ls(g_cls == KC_CLS_TAIL ? KC_CLS_TAIL : KC_LAYERNORM, st);
   if (H == 768)
     mv::layernorm_rows_kernel<6><<<blocks, 256, 0, st>>>(y, g, b, eps, x32, x32_stride, reinterpret_cast<__half*>(x16), M);
   else if (H == 128)
@@ -403,20 +420,23 @@ int layernorm_impl(const float* y, const float* g, const float* b, float eps, fl
   return MEMVUL_OK;
 }
 
-int embed_impl(const memvul_bert_weights* w, const int64_t* ids, const int64_t* tids, int B, int S, float* x32,
-               void* x16, cudaStream_t st) {
-  const int M = B * S;
-  const int blocks = (M + 7) / 8;
+int embed_impl(const memvul_bert_weights* w, const int64_t* ids, const int64_t* tids, const int32_t* lens,
+               const int32_t* row_start, int B, int S, float* x32, void* x16, int32_t* bad, cudaStream_t st) {
+  // 8 token rows per block, blocks never straddle sequences; packed layout: + 32 tail blocks that zero-fill the rows
+  // up to the next 256-row tile boundary
+  const int blocks = B * ((S + 7) / 8) + (row_start ? 32 : 0);
   auto ll = [](const int64_t* p) { return reinterpret_cast<const long long*>(p); };
   LaunchScope ls(KC_EMBED_LN, st);
   if (w->hidden == 768)
     mv::embed_layernorm_kernel<6><<<blocks, 256, 0, st>>>(ll(ids), ll(tids), w->word_emb, w->pos_emb, w->type_emb,
                                                           w->emb_ln_g, w->emb_ln_b, w->ln_eps, x32,
-                                                          reinterpret_cast<__half*>(x16), M, S, w->vocab, w->type_vocab);
+                                                          reinterpret_cast<__half*>(x16), B, S, w->vocab, w->type_vocab,
+                                                          lens, row_start, bad);
   else if (w->hidden == 128)
     mv::embed_layernorm_kernel<1><<<blocks, 256, 0, st>>>(ll(ids), ll(tids), w->word_emb, w->pos_emb, w->type_emb,
                                                           w->emb_ln_g, w->emb_ln_b, w->ln_eps, x32,
-                                                          reinterpret_cast<__half*>(x16), M, S, w->vocab, w->type_vocab);
+                                                          reinterpret_cast<__half*>(x16), B, S, w->vocab, w->type_vocab,
+                                                          lens, row_start, bad);
   else
     return fail(MEMVUL_E_INVALID, "embedding supports hidden in {128, 768}, got %d", w->hidden);
   CUDA_TRY(cudaGetLastError());
@@ -436,16 +456,56 @@ __global__ void mask_to_lens_kernel(const uint8_t* __restrict__ mask, int B, int
   }
   if (lane == 0) {
     lens[b] = cnt;
-    if (cnt == 0 || last != cnt - 1) *bad = 1;     // empty, or not a prefix mask
+    if (cnt == 0 || last != cnt - 1) atomicOr(bad, 1);     // empty, or not a prefix mask
   }
+}
+
+// row_start[0..B] = exclusive prefix sum of lens (one block; B is a batch size, at most a few thousand)
+__global__ void __launch_bounds__(1024) lens_to_row_start_kernel(const int32_t* __restrict__ lens, int B,
+                                                                 int32_t* __restrict__ row_start) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < B ? lens[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;                                   // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = x + (wid ? warp_tot[wid - 1] : 0) + carry;
+    if (i < B) row_start[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_start[B] = carry_s;
 }
 
 struct Workspace {
   __half* x16; __half* qkv; __half* ctx; __half* ffn;
   float* x32_cls; __half* x16_cls; __half* ctx_cls; __half* ffn_cls;     // [B, *] rows of the CLS-only last layer
+  float* x32_packed;                                                      // packed residual stream (PACKED without CLS_ONLY)
   size_t bytes;
 };
-Workspace carve(const memvul_bert_weights* w, int B, int S, void* base) {
+Workspace carve(const memvul_bert_weights* w, int B, int S, void* base, int flags) {
   const size_t M = static_cast<size_t>(B) * S, H = w->hidden, I = w->intermediate;
   auto up = [](size_t x) { return (x + 1023) & ~size_t(1023); };
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
@@ -460,6 +520,10 @@ Workspace carve(const memvul_bert_weights* w, int B, int S, void* base) {
   ws.x16_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * H * 2);
   ws.ctx_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * H * 2);
   ws.ffn_cls = reinterpret_cast<__half*>(p + off); off += up(Bp * I * 2);
+  ws.x32_packed = nullptr;
+  if ((flags & MEMVUL_ENC_PACKED) && !(flags & MEMVUL_ENC_CLS_ONLY)) {
+    ws.x32_packed = reinterpret_cast<float*>(p + off); off += up(M * H * 4);
+  }
   ws.bytes = off;
   return ws;
 }
@@ -480,9 +544,9 @@ extern "C" {
 int memvul_abi_version(void) { return MEMVUL_ABI_VERSION; }
 const char* memvul_last_error(void) { return g_err; }
 
-size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S) {
+size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S, int flags) {
   if (!w || B <= 0 || S <= 0) return 0;
-  return carve(w, B, S, nullptr).bytes;
+  return carve(w, B, S, nullptr, flags).bytes;
 }
 
 int memvul_gemm_f16(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
@@ -499,9 +563,10 @@ int memvul_gemm_ln_f16(const void* a, const void* w, const float* bias, const fl
   return rc;
 }
 
-int memvul_attention_f16(const void* qkv, const int32_t* lens, void* ctx, int B, int S, int H, void* stream) {
+int memvul_attention_f16(const void* qkv, const int32_t* lens, const int32_t* row_start, void* ctx, int B, int S,
+                         int H, void* stream) {
   if (!qkv || !lens || !ctx) return fail(MEMVUL_E_INVALID, "attention null pointer");
-  return attention_impl(qkv, lens, ctx, B, S, H, static_cast<cudaStream_t>(stream));
+  return attention_impl(qkv, lens, row_start, ctx, B, S, H, static_cast<cudaStream_t>(stream));
 }
 
 int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16, int M,
@@ -510,77 +575,96 @@ int memvul_layernorm(const float* y, const float* gamma, const float* beta, floa
   return layernorm_impl(y, gamma, beta, eps, x32, x16, M, H, static_cast<cudaStream_t>(stream));
 }
 
-int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids, int B,
-                           int S, float* x32, void* x16, void* stream) {
+int memvul_embed_layernorm(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
+                           const int32_t* lens, const int32_t* row_start, int B, int S, float* x32, void* x16,
+                           int32_t* bad_flag, void* stream) {
   if (!w || !token_ids || !x32 || !x16) return fail(MEMVUL_E_INVALID, "embed null pointer");
   if (B <= 0 || S <= 0 || S > w->max_pos) return fail(MEMVUL_E_INVALID, "embed needs 1 <= S <= max_pos (B=%d S=%d)", B, S);
-  return embed_impl(w, token_ids, type_ids, B, S, x32, x16, static_cast<cudaStream_t>(stream));
+  if (row_start && !lens) return fail(MEMVUL_E_INVALID, "embed: the packed layout needs lens as well as row_start");
+  return embed_impl(w, token_ids, type_ids, lens, row_start, B, S, x32, x16, bad_flag, static_cast<cudaStream_t>(stream));
 }
 
-int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* bad_flag, void* stream) {
+int memvul_mask_to_lens(const uint8_t* mask, int B, int S, int32_t* lens, int32_t* row_start, int32_t* bad_flag,
+                        void* stream) {
   if (!mask || !lens || !bad_flag || B <= 0 || S <= 0) return fail(MEMVUL_E_INVALID, "mask_to_lens bad argument");
-  LaunchScope ls(KC_OTHER, static_cast<cudaStream_t>(stream));
-  mask_to_lens_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, S, lens, bad_flag);
-  CUDA_TRY(cudaGetLastError());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls(KC_OTHER, st);
+    mask_to_lens_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, B, S, lens, bad_flag);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (row_start) {
+    LaunchScope ls(KC_OTHER, st);
+    lens_to_row_start_kernel<<<1, 1024, 0, st>>>(lens, B, row_start);
+    CUDA_TRY(cudaGetLastError());
+  }
   return MEMVUL_OK;
 }
 
 int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
-                           const int32_t* lens, int B, int S, float* hidden_out, void* workspace,
-                           size_t workspace_bytes, int flags, void* stream) {
+                           const int32_t* lens, const int32_t* row_start, int B, int S, float* hidden_out,
+                           void* workspace, size_t workspace_bytes, int flags, int32_t* bad_flag, void* stream) {
   if (int rc = check_weights(w)) return rc;
   if (!token_ids || !lens || !hidden_out || !workspace) return fail(MEMVUL_E_INVALID, "encoder null pointer");
   if (B <= 0 || S <= 0 || S > 512 || S > w->max_pos)
     return fail(MEMVUL_E_INVALID, "encoder needs 1 <= S <= min(512, max_pos) (B=%d S=%d)", B, S);
-  Workspace ws = carve(w, B, S, workspace);
+  const bool cls_only = (flags & MEMVUL_ENC_CLS_ONLY) != 0;
+  const bool packed = (flags & MEMVUL_ENC_PACKED) != 0;
+  if (packed && !row_start) return fail(MEMVUL_E_INVALID, "MEMVUL_ENC_PACKED needs row_start (memvul_mask_to_lens fills it)");
+  Workspace ws = carve(w, B, S, workspace, flags);
   if (ws.bytes > workspace_bytes)
     return fail(MEMVUL_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int M = B * S, H = w->hidden, I = w->intermediate;
-  float* x32 = hidden_out;
-  if (int rc = embed_impl(w, token_ids, type_ids, B, S, x32, ws.x16, st)) return rc;
-  const bool cls_only = (flags & MEMVUL_ENC_CLS_ONLY) != 0;
+  const int M = B * S, H = w->hidden, I = w->intermediate;     // M: row count (padded) or its upper bound (packed)
+  const int32_t* rs = packed ? row_start : nullptr;
+  const int* m_dev = packed ? row_start + B : nullptr;           // device-side row count T = sum(lens)
+  // residual stream: the caller's hidden_out, except for a packed full-output run (unpacked at the end)
+  float* x32 = (packed && !cls_only) ? ws.x32_packed : hidden_out;
+  if (int rc = embed_impl(w, token_ids, type_ids, lens, rs, B, S, x32, ws.x16, bad_flag, st)) return rc;
   for (int l = 0; l < w->layers; ++l) {
     const memvul_bert_layer& L = w->layer[l];
     if (cls_only && l == w->layers - 1) {
       // Last layer, [CLS]-only tail: keys/values need every row, but only query row 0 of each sequence is consumed
       // downstream, so attention runs on the first query tile and everything after it on B gathered rows.
       { ClassScope cs(KC_GEMM_QKV);
-      if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
-      if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st, /*first_tile_only=*/true)) return rc;
-      { LaunchScope ls(KC_OTHER, st);
-        mv::gather_cls_rows_kernel<<<B, 192, 0, st>>>(x32, ws.ctx, ws.x32_cls, ws.ctx_cls, B, S, H);
+      if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st, m_dev)) return rc; }
+      if (int rc = attention_impl(ws.qkv, lens, rs, ws.ctx, B, S, H, st, /*first_tile_only=*/true)) return rc;
+      ClassScope tail(KC_CLS_TAIL);              // the B-row launches are accounted apart from the full-size classes
+      { LaunchScope ls(KC_CLS_TAIL, st);
+        mv::gather_cls_rows_kernel<<<B, 192, 0, st>>>(x32, ws.ctx, ws.x32_cls, ws.ctx_cls, rs, B, S, H);
         CUDA_TRY(cudaGetLastError()); }
-      { ClassScope cs(KC_GEMM_ATTN_OUT);
-      if (int rc = gemm_impl(ws.ctx_cls, L.w_ao, L.b_ao, ws.x32_cls, ws.x32_cls, B, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
+      if (int rc = gemm_impl(ws.ctx_cls, L.w_ao, L.b_ao, ws.x32_cls, ws.x32_cls, B, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
       if (int rc = layernorm_impl(ws.x32_cls, L.ln1_g, L.ln1_b, w->ln_eps, ws.x32_cls, ws.x16_cls, B, H, st)) return rc;
-      { ClassScope cs(KC_GEMM_FFN_UP);
-      if (int rc = gemm_impl(ws.x16_cls, L.w_ff1, L.b_ff1, nullptr, ws.ffn_cls, B, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc; }
-      { ClassScope cs(KC_GEMM_FFN_DOWN);
-      if (int rc = gemm_impl(ws.ffn_cls, L.w_ff2, L.b_ff2, ws.x32_cls, ws.x32_cls, B, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc; }
-      // final LayerNorm scatters row b into hidden_out[b*S] (the [CLS] slot); other rows keep layer L-1 values
-      if (int rc = layernorm_impl(ws.x32_cls, L.ln2_g, L.ln2_b, w->ln_eps, x32, nullptr, B, H, st, (long long)S * H)) return rc;
+      if (int rc = gemm_impl(ws.x16_cls, L.w_ff1, L.b_ff1, nullptr, ws.ffn_cls, B, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc;
+      if (int rc = gemm_impl(ws.ffn_cls, L.w_ff2, L.b_ff2, ws.x32_cls, ws.x32_cls, B, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc;
+      // final LayerNorm scatters row b into hidden_out[b*S] (the [CLS] slot of the padded layout)
+      if (int rc = layernorm_impl(ws.x32_cls, L.ln2_g, L.ln2_b, w->ln_eps, hidden_out, nullptr, B, H, st, (long long)S * H)) return rc;
       break;
     }
     { ClassScope cs(KC_GEMM_QKV);
-    if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st)) return rc; }
-    if (int rc = attention_impl(ws.qkv, lens, ws.ctx, B, S, H, st)) return rc;
+    if (int rc = gemm_impl(ws.x16, L.w_qkv, L.b_qkv, nullptr, ws.qkv, M, 3 * H, H, MEMVUL_EPI_BIAS_F16, st, m_dev)) return rc; }
+    if (int rc = attention_impl(ws.qkv, lens, rs, ws.ctx, B, S, H, st)) return rc;
     { ClassScope cs(KC_GEMM_ATTN_OUT);
-      int rc = gemm_ln_impl(ws.ctx, L.w_ao, L.b_ao, x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, H, st);
+      int rc = gemm_ln_impl(ws.ctx, L.w_ao, L.b_ao, x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, H, st, m_dev);
       if (rc < 0) return rc;
       if (rc == 1) {      // shape not covered by the fused kernel: GEMM + stand-alone LayerNorm
-        if (int rc2 = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc2;
+        if (int rc2 = gemm_impl(ws.ctx, L.w_ao, L.b_ao, x32, x32, M, H, H, MEMVUL_EPI_BIAS_RESID_F32, st, m_dev)) return rc2;
         if (int rc2 = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc2;
       } }
     { ClassScope cs(KC_GEMM_FFN_UP);
-    if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st)) return rc; }
+    if (int rc = gemm_impl(ws.x16, L.w_ff1, L.b_ff1, nullptr, ws.ffn, M, I, H, MEMVUL_EPI_BIAS_GELU_F16, st, m_dev)) return rc; }
     { ClassScope cs(KC_GEMM_FFN_DOWN);
-      int rc = gemm_ln_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, I, st);
+      int rc = gemm_ln_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, I, st, m_dev);
       if (rc < 0) return rc;
       if (rc == 1) {
-        if (int rc2 = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st)) return rc2;
+        if (int rc2 = gemm_impl(ws.ffn, L.w_ff2, L.b_ff2, x32, x32, M, H, I, MEMVUL_EPI_BIAS_RESID_F32, st, m_dev)) return rc2;
         if (int rc2 = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, ws.x16, M, H, st)) return rc2;
       } }
+  }
+  if (packed && !cls_only) {          // packed residual stream -> the padded [B,S,H] tensor the interface returns
+    LaunchScope ls(KC_OTHER, st);
+    mv::unpack_rows_kernel<<<(M + 7) / 8, 256, 0, st>>>(ws.x32_packed, row_start, lens, hidden_out, B, S, H);
+    CUDA_TRY(cudaGetLastError());
   }
   return MEMVUL_OK;
 }
@@ -639,15 +723,16 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   const bool tiled = tiled_ok && (phase_mask & MEMVUL_PM_MATCH) && D == mv::MatchTileCfg::D && B >= 32 &&
                      static_cast<long long>(B) * G >= (1LL << 18);
   const int dyn_smem = tiled ? mv::MatchTileCfg::SMEM_BYTES : 0;
-  static int blocks_per_sm[2] = {0, 0};
-  if (blocks_per_sm[tiled] == 0) {
-    if (tiled) CUDA_TRY(cudaFuncSetAttribute(mv::pool_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+  if (tiled)
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::pool_match_kernel), dyn_smem)) return rc;
+  int& bps = *per_device_slot(tiled ? 2 : 1);
+  if (bps == 0) {
     int n = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mv::pool_match_kernel, 256, dyn_smem));
     if (n < 1) return fail(MEMVUL_E_CUDA, "pool_match kernel does not fit on an SM");
-    blocks_per_sm[tiled] = n > 4 ? 4 : n;
+    bps = n > 4 ? 4 : n;
   }
-  const int grid = di.sms * blocks_per_sm[tiled];
+  const int grid = di.sms * bps;
   const int nwarps = grid * 8;
   mv::PoolMatchParams p;
   p.cls = cls; p.cls_stride = cls_stride;

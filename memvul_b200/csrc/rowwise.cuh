@@ -64,50 +64,95 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* y, con
                x16 ? x16 + static_cast<size_t>(row) * H : nullptr, lane);
 }
 
-// Gather one row per sequence (row b*S of a [B*S, H] matrix) into dense [B, H] matrices: the [CLS] rows that the last
-// encoder layer's output projection / FFN actually need (BertPooler reads hidden[:,0] only, model_memory.py:99).
+// Gather one row per sequence (row b*S -- or row_start[b] in the packed layout -- of a token-major matrix) into dense
+// [B, H] matrices: the [CLS] rows that the last encoder layer's output projection / FFN actually need (BertPooler
+// reads hidden[:,0] only, model_memory.py:99).
 __global__ void __launch_bounds__(256) gather_cls_rows_kernel(const float* __restrict__ x32, const __half* __restrict__ c16,
                                                               float* __restrict__ x32_cls, __half* __restrict__ c16_cls,
-                                                              int B, int S, int H) {
+                                                              const int* __restrict__ row_start, int B, int S, int H) {
   const int b = blockIdx.x;
-  const size_t src = static_cast<size_t>(b) * S * H, dst = static_cast<size_t>(b) * H;
+  const size_t src = (row_start ? static_cast<size_t>(row_start[b]) : static_cast<size_t>(b) * S) * H;
+  const size_t dst = static_cast<size_t>(b) * H;
   for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
     *reinterpret_cast<float4*>(x32_cls + dst + i) = *reinterpret_cast<const float4*>(x32 + src + i);
     *reinterpret_cast<uint2*>(c16_cls + dst + i) = *reinterpret_cast<const uint2*>(c16 + src + i);
   }
 }
 
-// K1: LN(word[ids] + pos[s] + type[tt]).  ids / type_ids are int64 [B*S] as AllenNLP's
+// Packed (token-major) residual stream -> the padded [B,S,H] tensor the embedder interface returns
+// (custom_PTM_embedder.py:235); padded positions are zero-filled.  One warp per output row.
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ xp, const int* __restrict__ row_start,
+                                                          const int* __restrict__ lens, float* __restrict__ out, int B,
+                                                          int S, int H) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * S) return;
+  const int b = row / S, s = row - b * S;
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(row) * H);
+  if (s < lens[b]) {
+    const float4* src = reinterpret_cast<const float4*>(xp + (static_cast<size_t>(row_start[b]) + s) * H);
+    for (int i = lane; i < H / 4; i += 32) dst[i] = src[i];
+  } else {
+    for (int i = lane; i < H / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// K1: LN(word[ids] + pos[s] + type[tt]).  ids / type_ids are int64 [B,S] (padded) as AllenNLP's
 // PretrainedTransformerIndexer produces them; type_ids == nullptr means all-zero
-// (custom_PTM_embedder.py:199-202).  Out-of-range ids are clamped to [0, vocab) on the device;
-// the host wrapper rejects them up front.
+// (custom_PTM_embedder.py:199-202).  Out-of-range ids are clamped AND reported: bit 1 of *bad is set, which the host
+// turns into the error the reference raises (torch.embedding index error; custom_PTM_embedder.py:205 for type ids).
+// Padded layout (row_start == nullptr): output row b*S + s for every s < S.
+// Packed layout: only s < lens[b] is computed and lands at row row_start[b] + s; the rows between the last token and
+// the next 256-row GEMM tile boundary are zero-filled so that nothing non-finite can enter a partially filled tile.
 template <int NV>
 __global__ void __launch_bounds__(256) embed_layernorm_kernel(
     const long long* __restrict__ ids, const long long* __restrict__ type_ids, const float* __restrict__ word,
     const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float eps, float* __restrict__ x32, __half* __restrict__ x16, int M, int S,
-    int vocab, int type_vocab) {
+    const float* __restrict__ beta, float eps, float* __restrict__ x32, __half* __restrict__ x16, int B, int S,
+    int vocab, int type_vocab, const int* __restrict__ lens, const int* __restrict__ row_start, int* __restrict__ bad) {
   constexpr int H = NV * 128;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  long long id = ids[row];
-  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  long long tt = type_ids ? type_ids[row] : 0;
-  tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
+  const int chunks = (S + 7) >> 3;                          // 8 rows (warps) per block, blocks never straddle sequences
+  const int b = blockIdx.x / chunks;
+  const int s = (blockIdx.x - b * chunks) * 8 + (threadIdx.x >> 5);
+  if (b >= B) {
+    // packed layout only: tail blocks zero-fill rows [T, round_up(T, 256)) (clipped to the buffer)
+    const int T = row_start[B];
+    const int r = T + (blockIdx.x - B * chunks) * 8 + (threadIdx.x >> 5);
+    const int end = min(((T + 255) >> 8) << 8, B * S);
+    if (r < end) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = i * 128 + lane * 4;
+        *reinterpret_cast<float4*>(x32 + static_cast<size_t>(r) * H + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<uint2*>(x16 + static_cast<size_t>(r) * H + col) = make_uint2(0u, 0u);
+      }
+    }
+    return;
+  }
+  if (s >= S || (row_start && s >= lens[b])) return;
+  const size_t in_row = static_cast<size_t>(b) * S + s;
+  const size_t out_row = row_start ? static_cast<size_t>(row_start[b]) + s : in_row;
+  long long id = ids[in_row];
+  long long tt = type_ids ? type_ids[in_row] : 0;
+  if (id < 0 || id >= vocab || tt < 0 || tt >= type_vocab) {
+    if (lane == 0 && bad) atomicOr(bad, 2);
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
+  }
   const float* w = word + static_cast<size_t>(id) * H;
-  const float* p = pos + static_cast<size_t>(row % S) * H;
+  const float* p = pos + static_cast<size_t>(s) * H;
   const float* t = type + static_cast<size_t>(tt) * H;
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = i * 128 + lane * 4;
     const float4 a = __ldg(reinterpret_cast<const float4*>(w + col));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p + col));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(p + col));
     const float4 c = __ldg(reinterpret_cast<const float4*>(t + col));
-    v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+    v[i] = make_float4((a.x + bb.x) + c.x, (a.y + bb.y) + c.y, (a.z + bb.z) + c.z, (a.w + bb.w) + c.w);
   }
-  ln_store<NV>(v, gamma, beta, eps, x32 + static_cast<size_t>(row) * H, x16 + static_cast<size_t>(row) * H, lane);
+  ln_store<NV>(v, gamma, beta, eps, x32 + out_row * H, x16 + out_row * H, lane);
 }
 
 }  // namespace mv

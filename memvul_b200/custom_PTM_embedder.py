@@ -22,6 +22,8 @@ from . import native
 from .modules import BertConfigLite, BertWeights, params_version
 from .registrable import TokenEmbedder
 
+_PACKED_DEFAULT = os.environ.get("MEMVUL_ENC_PACKED", "1") != "0"
+
 
 @TokenEmbedder.register("custom_pretrained_transformer")
 class PretrainedTransformerEmbedder(TokenEmbedder):
@@ -88,20 +90,29 @@ class PretrainedTransformerEmbedder(TokenEmbedder):
             self._packed_version = ver
         return self._packed
 
-    def workspace(self, B: int, S: int, device: torch.device) -> torch.Tensor:
-        need = self.packed().workspace_bytes(B, S)
+    def workspace(self, B: int, S: int, device: torch.device, flags: int = 0) -> torch.Tensor:
+        need = self.packed().workspace_bytes(B, S, flags)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+            # zero-initialised once (include/memvul_b200.h: the packed execution reads rows past the last token of a
+            # partially filled tile, which must be finite); grown geometrically so a stream of growing batches
+            # does not reallocate every step
+            grow = 0 if self._workspace is None or self._workspace.device != device else self._workspace.numel() * 5 // 4
+            self._workspace = None
+            self._workspace = torch.zeros(max(need, grow), dtype=torch.uint8, device=device)
         return self._workspace
 
     def encode(self, token_ids: torch.Tensor, lens: torch.Tensor, type_ids: Optional[torch.Tensor] = None,
-               out: Optional[torch.Tensor] = None, cls_only: bool = False) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, cls_only: bool = False,
+               row_start: Optional[torch.Tensor] = None, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B,S] ids + per-sequence lengths -> fp32 [B,S,H]; asynchronous on the current stream.
-        ``cls_only``: only ``[:, 0]`` is the final layer's output (enough for BertPooler)."""
+        ``cls_only``: only ``[:, 0]`` is the final layer's output (enough for BertPooler).
+        ``row_start``: packed var-len execution (padded tokens are never computed)."""
         B, S = token_ids.shape
+        flags = (native.ENC_CLS_ONLY if cls_only else 0) | (native.ENC_PACKED if row_start is not None else 0)
         return native.encoder_forward(self.packed(), token_ids.contiguous(), lens,
                                       None if type_ids is None else type_ids.contiguous(),
-                                      self.workspace(B, S, token_ids.device), out, cls_only=cls_only)
+                                      self.workspace(B, S, token_ids.device, flags), out, cls_only=cls_only,
+                                      row_start=row_start, bad=bad)
 
     # ------------------------------------------------------------------ reference interface
     def forward(self, token_ids: torch.LongTensor, mask: torch.BoolTensor,
@@ -114,9 +125,20 @@ class PretrainedTransformerEmbedder(TokenEmbedder):
             raise ValueError("token_ids and mask must have the same shape")
         if type_ids is not None and token_ids.shape != type_ids.shape:
             raise ValueError("token_ids and type_ids must have the same shape")       # :205-206
-        lens, bad = native.mask_to_lens(mask.contiguous())
-        hidden = self.encode(token_ids, lens, type_ids, cls_only=cls_only)
-        # The reference's `type_ids.max()` (:199-202) is a host sync per batch; the checks are deferred to
-        # the caller's first host read instead (ModelMemory bundles them with its result copy).
+        # Packed (token-major, var-len) execution is the default: the reference pads every batch to its longest member
+        # (config_memory.json:50-57) and pays for the padding in every GEMM; here padded tokens are never computed and
+        # the row count stays on the device (no host sync).  MEMVUL_ENC_PACKED=0 selects the padded execution.
+        if _PACKED_DEFAULT:
+            lens, row_start, bad = native.mask_to_lens(mask.contiguous(), with_row_start=True)
+        else:
+            (lens, bad), row_start = native.mask_to_lens(mask.contiguous()), None
+        hidden = self.encode(token_ids, lens, type_ids, cls_only=cls_only, row_start=row_start, bad=bad)
+        # The reference's `type_ids.max()` (:199-202) is a host sync per batch, and torch.embedding raises on an
+        # out-of-range id; here both checks (and the prefix-mask check) set bits of a device flag that the caller reads
+        # with its results (ModelMemory bundles it with the result copy; native.raise_for_flag turns it into the error).
         self.last_bad_mask_flag = bad
         return hidden
+
+    def check_last_batch(self) -> None:
+        """Synchronising check of the deferred flag of the last ``forward`` (mask not a prefix mask / id out of range)."""
+        native.raise_for_flag(int(self.last_bad_mask_flag.item()))

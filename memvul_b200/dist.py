@@ -75,3 +75,72 @@ def gather_match(result: Dict[str, torch.Tensor], counts: Sequence[int], group: 
         g = result["probs"].shape[1]
         out["probs"] = packed[:, 3:].reshape(-1, g, 2)
     return out
+
+
+class AsyncGather:
+    """The sharded path's collective, off the compute stream.
+
+    Round 1 issued pack (torch.cat) -> all-gather -> unpack on the compute stream after every batch: ~5 tiny launches
+    plus NCCL's launch latency, a fixed ~0.4 ms tail per step that was the whole 5 % weak-scaling loss.  Here the shard
+    result already is one flat buffer (``ModelMemory.match_batch(..., flat_capacity=max(counts))``,
+    ``native.match_flat_layout``), so the exchange is exactly ONE ``all_gather_into_tensor`` with nothing around it, and
+    it is enqueued on a side stream that waits for the batch's match kernel: step i's gather overlaps step i+1's encoder.
+    ``wait()`` makes the caller's stream wait for the last submitted gather and returns its decoded views."""
+
+    def __init__(self, counts: Sequence[int], device: torch.device, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.counts, self.cap, self.group, self.device = list(counts), max(counts), group, device
+        self.world = dist.get_world_size(group)
+        self.stream = torch.cuda.Stream(device) if torch.device(device).type == "cuda" else None
+        self.pending = None
+
+    def submit(self, result: Dict[str, torch.Tensor]) -> None:
+        flat = result.get("_flat")
+        if flat is None or result.get("_flat_capacity") != self.cap:
+            raise ValueError("AsyncGather.submit needs a result produced with flat_capacity=max(counts)")
+        G = result["probs"].shape[1]
+        out = flat.new_empty(self.world * flat.numel())
+        if self.stream is None:                                   # CPU tensors (gloo tests): plain synchronous gather
+            dist.all_gather_into_tensor(out, flat, group=self.group)
+        else:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev)
+                dist.all_gather_into_tensor(out, flat, group=self.group)
+            flat.record_stream(self.stream)
+            out.record_stream(self.stream)
+        self.pending = (out, G, flat.numel())
+
+    def wait(self) -> Optional[Dict[str, List[torch.Tensor]]]:
+        if self.pending is None:
+            return None
+        out, G, n = self.pending
+        self.pending = None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return decode_flat(out, self.counts, self.cap, G, n)
+
+
+def decode_flat(out: torch.Tensor, counts: Sequence[int], cap: int, G: int, n: int) -> Dict[str, List[torch.Tensor]]:
+    """Views (no copies) into the gathered flat buffers: per rank r, probs [counts[r],G,2], best_probs [counts[r],2],
+    best_idx [counts[r]] int32."""
+    from .native import match_flat_layout
+    o_bp, o_bi, n_chk = match_flat_layout(cap, G)
+    if n_chk != n:
+        raise ValueError("flat buffer size does not match the layout")
+    res: Dict[str, List[torch.Tensor]] = {"probs": [], "best_probs": [], "best_idx": []}
+    for r, c in enumerate(counts):
+        base = out[r * n:(r + 1) * n]
+        res["probs"].append(base[:c * G * 2].view(c, G, 2))
+        res["best_probs"].append(base[o_bp:o_bp + c * 2].view(c, 2))
+        res["best_idx"].append(base[o_bi:o_bi + c].view(torch.int32))
+    return res
+
+
+def gather_match_flat(result: Dict[str, torch.Tensor], counts: Sequence[int],
+                      group: Optional[dist.ProcessGroup] = None) -> Dict[str, torch.Tensor]:
+    """Synchronous form of AsyncGather for callers that want concatenated tensors: one all-gather of the flat buffer."""
+    ag = AsyncGather(counts, result["_flat"].device, group)
+    ag.submit(result)
+    parts = ag.wait()
+    return {k: torch.cat(v) for k, v in parts.items()}

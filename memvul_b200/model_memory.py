@@ -104,7 +104,8 @@ class ModelMemory(Model):
         self._projector = nn.Linear(3 * embedding_dim, 2, bias=False)
         self._temperature = temperature
 
-        self._golden_instances_embeddings: Optional[torch.Tensor] = None
+        self._bank: Optional[torch.Tensor] = None
+        self._bank_generation = 0     # bumped by every assignment to _golden_instances_embeddings (incl. reset to None)
         self._golden_instances_labels: Optional[List[str]] = None
         self._vterm = None            # (key, tensor) cache of Wv . bank
 
@@ -116,6 +117,19 @@ class ModelMemory(Model):
             initializer(self)
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def _golden_instances_embeddings(self) -> Optional[torch.Tensor]:
+        """The external memory [G, header_dim]; assigned from outside too (MemVul/callbacks.py:48-49 resets it to
+        None every epoch).  Every assignment invalidates the cached Wv . bank term: the bank is written through raw
+        pointers / torch.cat, so neither its address nor its _version identify its contents."""
+        return self._bank
+
+    @_golden_instances_embeddings.setter
+    def _golden_instances_embeddings(self, value) -> None:
+        self._bank = value
+        self._bank_generation += 1
+        self._vterm = None
+
     @property
     def embedder(self):
         return self._text_field_embedder.embedder("tokens")
@@ -152,8 +166,7 @@ class ModelMemory(Model):
     def forward_gold_instances(self, sample, metadata) -> None:
         """model_memory.py:105-115: append the anchors' feature vectors / labels to the external memory."""
         embedding = self._instance_forward(sample, use_header=self._use_header)
-        if int(self._last_bad.item()):
-            raise ValueError("anchor batch has a mask that is not a non-empty prefix mask")
+        native.raise_for_flag(int(self._last_bad.item()))
         labels = [m["instance"][0]["label"] for m in metadata]
         if not torch.is_tensor(self._golden_instances_embeddings):
             self._golden_instances_embeddings = embedding
@@ -164,7 +177,7 @@ class ModelMemory(Model):
 
     def _bank_vterm(self) -> torch.Tensor:
         bank = self._golden_instances_embeddings
-        key = (bank.data_ptr(), tuple(bank.shape), bank._version, self._projector.weight.data_ptr(),
+        key = (self._bank_generation, tuple(bank.shape), self._projector.weight.data_ptr(),
                self._projector.weight._version)
         if self._vterm is None or self._vterm[0] != key:
             self._vterm = (key, native.bank_prepare(bank.contiguous(), self._projector.weight.contiguous()))
@@ -204,8 +217,7 @@ class ModelMemory(Model):
         ev.record()
 
         def check():
-            if int(flag_h[0]):
-                raise ValueError("batch has a mask that is not a non-empty prefix mask (AllenNLP padding masks are)")
+            native.raise_for_flag(int(flag_h[0]))
 
         output_dict["probs"] = LazyHostArray(host["probs"], ev, check)           # list[B][G][2], model_memory.py:143
         output_dict["native"] = {"device": res, "best_probs": LazyHostArray(host["best_probs"], ev, check),
@@ -216,8 +228,10 @@ class ModelMemory(Model):
                               "metadata": metadata, "check": check})
         return output_dict
 
-    def match_batch(self, sample1) -> Dict[str, torch.Tensor]:
-        """Device-side result of the test branch: u, logits/probs [B,G,2], best_idx [B], best_probs [B,2]."""
+    def match_batch(self, sample1, flat_capacity: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Device-side result of the test branch: u, logits/probs [B,G,2], best_idx [B], best_probs [B,2].
+        ``flat_capacity``: lay probs / best_probs / best_idx out in one flat buffer (``native.match_flat_layout``) that
+        the multi-GPU gather sends without packing."""
         hidden, bad = self._encode(sample1)
         B, S, H = hidden.shape
         wp, bp, wh, bh = self._head_weights()
@@ -225,7 +239,8 @@ class ModelMemory(Model):
             raise NotImplementedError("use_header=False is not used by the MemVul configs")
         bank = self._golden_instances_embeddings
         out = native.pool_match(hidden, S * H, B, wp, bp, wh, bh, self._projector.weight, bank.contiguous(),
-                                self._bank_vterm(), same_idx=self._same_idx, phase_mask=native.PM_ALL)
+                                self._bank_vterm(), same_idx=self._same_idx, phase_mask=native.PM_ALL,
+                                flat_capacity=flat_capacity)
         out["bad_mask"] = bad
         return out
 

@@ -68,8 +68,7 @@ class ModelSingle(Model):
                                  self._bert_pooler.pooler.dense.bias, fc.weight, fc.bias,
                                  phase_mask=native.PM_POOL | native.PM_HEADER)
         logits, probs = native.single_head(head["u"], self._projector[1].weight.contiguous())
-        if int(emb.last_bad_mask_flag.item()):            # model_single returns host lists, so it syncs anyway (:92)
-            raise ValueError("batch has a mask that is not a non-empty prefix mask")
+        emb.check_last_batch()                            # model_single returns host lists, so it syncs anyway (:92)
         probs_h = probs.cpu()
         output_dict["probs"] = probs_h.tolist()
         output_dict["logits_device"] = logits

@@ -20,6 +20,7 @@ _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmemvul_b200.so")
 SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh", "rowwise.cuh", "pool_match.cuh"]
 
+ABI_VERSION = 2
 EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32 = 0, 1, 2
 PM_POOL, PM_HEADER, PM_UTERM, PM_MATCH, PM_FINAL, PM_ALL = 1, 2, 4, 8, 16, 31
 
@@ -71,7 +72,7 @@ EXPORTS = ["memvul_abi_version", "memvul_last_error", "memvul_encoder_workspace_
            "memvul_gemm_f16", "memvul_gemm_ln_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm",
            "memvul_launch_count", "memvul_profile_enable", "memvul_profile_read"]
 KERNEL_CLASSES = ["embed_ln", "gemm_qkv", "attention", "gemm_attn_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down",
-                  "pool_match", "other"]
+                  "pool_match", "other", "attention_cls", "cls_tail"]
 
 
 def lib() -> ctypes.CDLL:
@@ -86,26 +87,26 @@ def lib() -> ctypes.CDLL:
             L.memvul_abi_version.restype = ctypes.c_int
             L.memvul_last_error.restype = ctypes.c_char_p
             L.memvul_encoder_workspace_bytes.restype = ctypes.c_size_t
-            L.memvul_encoder_workspace_bytes.argtypes = [ctypes.POINTER(BertWeightsC), i32, i32]
-            L.memvul_encoder_forward.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, vp, i32, i32, vp, vp,
-                                                 ctypes.c_size_t, i32, vp]
-            L.memvul_mask_to_lens.argtypes = [vp, i32, i32, vp, vp, vp]
+            L.memvul_encoder_workspace_bytes.argtypes = [ctypes.POINTER(BertWeightsC), i32, i32, i32]
+            L.memvul_encoder_forward.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, vp, vp, i32, i32, vp, vp,
+                                                 ctypes.c_size_t, i32, vp, vp]
+            L.memvul_mask_to_lens.argtypes = [vp, i32, i32, vp, vp, vp, vp]
             L.memvul_bank_prepare.argtypes = [vp, vp, i32, i32, vp, vp]
             L.memvul_pool_match.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                             vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
             L.memvul_single_head.argtypes = [vp, vp, i32, i32, vp, vp, vp]
             L.memvul_gemm_f16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
             L.memvul_gemm_ln_f16.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]
-            L.memvul_attention_f16.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+            L.memvul_attention_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
             L.memvul_layernorm.argtypes = [vp, vp, vp, f32, vp, vp, i32, i32, vp]
-            L.memvul_embed_layernorm.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, i32, i32, vp, vp, vp]
+            L.memvul_embed_layernorm.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
             L.memvul_launch_count.restype = ctypes.c_longlong
             L.memvul_profile_enable.argtypes = [i32]
             L.memvul_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
             for name in EXPORTS:
                 if name not in ("memvul_last_error", "memvul_encoder_workspace_bytes", "memvul_launch_count"):
                     getattr(L, name).restype = ctypes.c_int
-            if L.memvul_abi_version() != 1:
+            if L.memvul_abi_version() != ABI_VERSION:
                 raise NativeError("libmemvul_b200.so ABI version mismatch")
             _lib = L
         return _lib
@@ -117,8 +118,16 @@ def _check(rc: int) -> None:
         raise (ValueError if rc == -1 else NativeError)(f"memvul_b200 native call failed ({rc}): {msg}")
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _on(t: torch.Tensor):
+    """Device guard: the kernels launch in the CURRENT CUDA context, so every native call runs with the device of its
+    tensors current (a model moved with ``.cuda(1)`` in a process whose current device is 0 must still work)."""
+    if not t.is_cuda:
+        raise NativeError("memvul_b200 has no CPU path: tensors must live on a CUDA device")
+    return torch.cuda.device(t.device)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -183,42 +192,63 @@ class PackedBert:
                               type_emb=self.type.data_ptr(), emb_ln_g=self.emb_g.data_ptr(),
                               emb_ln_b=self.emb_b.data_ptr(), layer=self._layer_arr)
 
-    def workspace_bytes(self, B: int, S: int) -> int:
-        return int(lib().memvul_encoder_workspace_bytes(ctypes.byref(self.c), B, S))
+    def workspace_bytes(self, B: int, S: int, flags: int = 0) -> int:
+        return int(lib().memvul_encoder_workspace_bytes(ctypes.byref(self.c), B, S, flags))
 
 
 # ------------------------------------------------------------------------------- calls
-def mask_to_lens(mask: torch.Tensor) -> torch.Tensor:
-    """bool [B,S] -> int32 [B]; raises ValueError on a mask that is not a non-empty prefix mask."""
+BAD_MASK, BAD_ID = 1, 2          # bits of the deferred error flag
+
+
+def mask_to_lens(mask: torch.Tensor, with_row_start: bool = False):
+    """bool [B,S] -> (lens int32 [B], bad int32 [1]) or, ``with_row_start``, (lens, row_start int32 [B+1], bad).
+    ``bad`` bit 0: some mask is not a non-empty prefix mask (read it with the batch's results; no sync here)."""
     _need(mask, torch.bool, "mask")
     B, S = mask.shape
     lens = torch.empty(B, dtype=torch.int32, device=mask.device)
+    row_start = torch.empty(B + 1, dtype=torch.int32, device=mask.device) if with_row_start else None
     bad = torch.zeros(1, dtype=torch.int32, device=mask.device)
-    _check(lib().memvul_mask_to_lens(mask.data_ptr(), B, S, lens.data_ptr(), bad.data_ptr(), _stream()))
-    return lens, bad
+    with _on(mask):
+        _check(lib().memvul_mask_to_lens(mask.data_ptr(), B, S, lens.data_ptr(), _ptr(row_start), bad.data_ptr(),
+                                         _stream(mask)))
+    return (lens, row_start, bad) if with_row_start else (lens, bad)
 
 
-ENC_CLS_ONLY = 1
+def raise_for_flag(flag: int) -> None:
+    """Turn the deferred device flag into the errors the reference raises."""
+    if flag & BAD_MASK:
+        raise ValueError("batch has a mask that is not a non-empty prefix mask (AllenNLP padding masks are)")
+    if flag & BAD_ID:
+        raise ValueError("token id or type id out of range for the embedding tables "
+                         "(torch.embedding raises in the reference; custom_PTM_embedder.py:205 for type ids)")
+
+
+ENC_CLS_ONLY, ENC_PACKED = 1, 2
 
 
 def encoder_forward(w: PackedBert, token_ids: torch.Tensor, lens: torch.Tensor,
                     type_ids: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                    out: Optional[torch.Tensor] = None, cls_only: bool = False) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, cls_only: bool = False,
+                    row_start: Optional[torch.Tensor] = None, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
     """last_hidden_state fp32 [B,S,H] of HF BertModel for prefix-masked inputs.  ``cls_only``: only row 0 of each
-    sequence is the last layer's output (what BertPooler consumes); the last layer skips the other rows."""
+    sequence is the last layer's output (what BertPooler consumes); the last layer skips the other rows.
+    ``row_start`` (from ``mask_to_lens(..., with_row_start=True)``) selects the packed var-len execution: padded
+    tokens are never computed.  ``bad``: device int32 flag that collects out-of-range ids."""
     _need(token_ids, torch.int64, "token_ids")
     _need(lens, torch.int32, "lens")
     if type_ids is not None:
         _need(type_ids, torch.int64, "type_ids")
     B, S = token_ids.shape
-    need = w.workspace_bytes(B, S)
+    flags = (ENC_CLS_ONLY if cls_only else 0) | (ENC_PACKED if row_start is not None else 0)
+    need = w.workspace_bytes(B, S, flags)
     if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=token_ids.device)
+        workspace = torch.zeros(need, dtype=torch.uint8, device=token_ids.device)   # zero-init: header contract (PACKED)
     if out is None:
         out = torch.empty(B, S, w.hidden, dtype=torch.float32, device=token_ids.device)
-    _check(lib().memvul_encoder_forward(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), lens.data_ptr(),
-                                        B, S, out.data_ptr(), workspace.data_ptr(), workspace.numel(),
-                                        ENC_CLS_ONLY if cls_only else 0, _stream()))
+    with _on(token_ids):
+        _check(lib().memvul_encoder_forward(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), lens.data_ptr(),
+                                            _ptr(row_start), B, S, out.data_ptr(), workspace.data_ptr(),
+                                            workspace.numel(), flags, _ptr(bad), _stream(token_ids)))
     return out
 
 
@@ -227,14 +257,26 @@ def bank_prepare(bank: torch.Tensor, w_proj: torch.Tensor) -> torch.Tensor:
     _need(w_proj, torch.float32, "w_proj")
     G, D = bank.shape
     vterm = torch.empty(G, 2, dtype=torch.float32, device=bank.device)
-    _check(lib().memvul_bank_prepare(bank.data_ptr(), w_proj.data_ptr(), G, D, vterm.data_ptr(), _stream()))
+    with _on(bank):
+        _check(lib().memvul_bank_prepare(bank.data_ptr(), w_proj.data_ptr(), G, D, vterm.data_ptr(), _stream(bank)))
     return vterm
+
+
+def match_flat_layout(cap: int, G: int):
+    """Offsets (in 4-byte words) of the sections of the flat result buffer of one shard with room for ``cap`` issue
+    reports: [probs cap*G*2 | best_probs cap*2 | best_idx cap (int32 bits)].  One contiguous buffer per shard means
+    the sharded path's single all-gather (memvul_b200/dist.py) needs no pack / unpack kernels."""
+    o_bp = cap * G * 2
+    o_bi = o_bp + cap * 2
+    return o_bp, o_bi, o_bi + cap
 
 
 def pool_match(cls: torch.Tensor, cls_stride: int, B: int, w_pool, b_pool, w_head, b_head, w_proj=None, bank=None,
                vterm=None, same_idx: int = 0, phase_mask: int = PM_ALL, u: Optional[torch.Tensor] = None,
-               pooled: Optional[torch.Tensor] = None):
-    """Fused pool + header + match.  Returns dict(u, pooled[, logits, probs, best_idx, best_probs])."""
+               pooled: Optional[torch.Tensor] = None, flat_capacity: Optional[int] = None):
+    """Fused pool + header + match.  Returns dict(u, pooled[, logits, probs, best_idx, best_probs]).
+    ``flat_capacity``: allocate probs / best_probs / best_idx as views of ONE flat fp32 buffer (``out["_flat"]``) laid
+    out by ``match_flat_layout(flat_capacity, G)`` -- what the multi-GPU gather sends as is."""
     dev = w_pool.device
     H = w_pool.shape[0]
     D = w_head.shape[0] if w_head is not None else 4
@@ -249,14 +291,24 @@ def pool_match(cls: torch.Tensor, cls_stride: int, B: int, w_pool, b_pool, w_hea
         best_key = torch.empty(B, dtype=torch.int64, device=dev)
     if phase_mask & (PM_MATCH | PM_FINAL):
         logits = torch.empty(B, G, 2, **f)
-        probs = torch.empty(B, G, 2, **f)
-        best_idx = torch.empty(B, dtype=torch.int32, device=dev)
-        best_probs = torch.empty(B, 2, **f)
+        if flat_capacity is not None:
+            cap = max(int(flat_capacity), B)
+            o_bp, o_bi, n = match_flat_layout(cap, G)
+            flat = torch.empty(n, **f)
+            probs = flat[:B * G * 2].view(B, G, 2)
+            best_probs = flat[o_bp:o_bp + B * 2].view(B, 2)
+            best_idx = flat[o_bi:o_bi + B].view(torch.int32)
+            out["_flat"], out["_flat_capacity"] = flat, cap
+        else:
+            probs = torch.empty(B, G, 2, **f)
+            best_idx = torch.empty(B, dtype=torch.int32, device=dev)
+            best_probs = torch.empty(B, 2, **f)
         out.update(logits=logits, probs=probs, best_idx=best_idx, best_probs=best_probs)
-    _check(lib().memvul_pool_match(_ptr(cls), cls_stride, _ptr(w_pool), _ptr(b_pool), _ptr(w_head), _ptr(b_head),
-                                   _ptr(w_proj), _ptr(bank), _ptr(vterm), B, G, H, D, same_idx, _ptr(pooled), _ptr(u),
-                                   _ptr(uterm), _ptr(best_key), _ptr(logits), _ptr(probs), _ptr(best_idx),
-                                   _ptr(best_probs), phase_mask, _stream()))
+    with _on(w_pool):
+        _check(lib().memvul_pool_match(_ptr(cls), cls_stride, _ptr(w_pool), _ptr(b_pool), _ptr(w_head), _ptr(b_head),
+                                       _ptr(w_proj), _ptr(bank), _ptr(vterm), B, G, H, D, same_idx, _ptr(pooled),
+                                       _ptr(u), _ptr(uterm), _ptr(best_key), _ptr(logits), _ptr(probs),
+                                       _ptr(best_idx), _ptr(best_probs), phase_mask, _stream(w_pool)))
     out["_scratch"] = (uterm, best_key)
     return out
 
@@ -267,8 +319,9 @@ def single_head(feat: torch.Tensor, w_cls: torch.Tensor):
     B, D = feat.shape
     logits = torch.empty(B, 2, dtype=torch.float32, device=feat.device)
     probs = torch.empty_like(logits)
-    _check(lib().memvul_single_head(feat.data_ptr(), w_cls.data_ptr(), B, D, logits.data_ptr(), probs.data_ptr(),
-                                    _stream()))
+    with _on(feat):
+        _check(lib().memvul_single_head(feat.data_ptr(), w_cls.data_ptr(), B, D, logits.data_ptr(), probs.data_ptr(),
+                                        _stream(feat)))
     return logits, probs
 
 
@@ -283,8 +336,9 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_BIAS_RESID_F32 else torch.float16,
                           device=a.device)
-    _check(lib().memvul_gemm_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid), out.data_ptr(), M, N, K,
-                                 epilogue, _stream()))
+    with _on(a):
+        _check(lib().memvul_gemm_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid), out.data_ptr(), M, N, K,
+                                     epilogue, _stream(a)))
     return out
 
 
@@ -298,16 +352,21 @@ def gemm_ln_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: tor
     N = w.shape[0]
     x32 = resid if inplace else torch.empty(M, N, dtype=torch.float32, device=a.device)
     x16 = torch.empty(M, N, dtype=torch.float16, device=a.device)
-    _check(lib().memvul_gemm_ln_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), gamma.data_ptr(),
-                                    beta.data_ptr(), eps, x32.data_ptr(), x16.data_ptr(), M, N, K, _stream()))
+    with _on(a):
+        _check(lib().memvul_gemm_ln_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), gamma.data_ptr(),
+                                        beta.data_ptr(), eps, x32.data_ptr(), x16.data_ptr(), M, N, K, _stream(a)))
     return x32, x16
 
 
-def attention_f16(qkv: torch.Tensor, lens: torch.Tensor, B: int, S: int, H: int) -> torch.Tensor:
+def attention_f16(qkv: torch.Tensor, lens: torch.Tensor, B: int, S: int, H: int,
+                  row_start: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``row_start`` None: qkv rows are the padded [B*S] layout; else the packed layout (rows row_start[b]..)."""
     _need(qkv, torch.float16, "qkv")
     _need(lens, torch.int32, "lens")
-    ctx = torch.empty(B * S, H, dtype=torch.float16, device=qkv.device)
-    _check(lib().memvul_attention_f16(qkv.data_ptr(), lens.data_ptr(), ctx.data_ptr(), B, S, H, _stream()))
+    ctx = torch.zeros(qkv.shape[0], H, dtype=torch.float16, device=qkv.device)
+    with _on(qkv):
+        _check(lib().memvul_attention_f16(qkv.data_ptr(), lens.data_ptr(), _ptr(row_start), ctx.data_ptr(), B, S, H,
+                                          _stream(qkv)))
     return ctx
 
 
@@ -316,18 +375,23 @@ def layernorm(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     M, H = y.shape
     x32 = torch.empty_like(y)
     x16 = torch.empty(M, H, dtype=torch.float16, device=y.device)
-    _check(lib().memvul_layernorm(y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, x32.data_ptr(),
-                                  x16.data_ptr(), M, H, _stream()))
+    with _on(y):
+        _check(lib().memvul_layernorm(y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, x32.data_ptr(),
+                                      x16.data_ptr(), M, H, _stream(y)))
     return x32, x16
 
 
-def embed_layernorm(w: PackedBert, token_ids: torch.Tensor, type_ids: Optional[torch.Tensor] = None):
+def embed_layernorm(w: PackedBert, token_ids: torch.Tensor, type_ids: Optional[torch.Tensor] = None,
+                    lens: Optional[torch.Tensor] = None, row_start: Optional[torch.Tensor] = None,
+                    bad: Optional[torch.Tensor] = None):
     _need(token_ids, torch.int64, "token_ids")
     B, S = token_ids.shape
-    x32 = torch.empty(B * S, w.hidden, dtype=torch.float32, device=token_ids.device)
-    x16 = torch.empty(B * S, w.hidden, dtype=torch.float16, device=token_ids.device)
-    _check(lib().memvul_embed_layernorm(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), B, S,
-                                        x32.data_ptr(), x16.data_ptr(), _stream()))
+    x32 = torch.zeros(B * S, w.hidden, dtype=torch.float32, device=token_ids.device)
+    x16 = torch.zeros(B * S, w.hidden, dtype=torch.float16, device=token_ids.device)
+    with _on(token_ids):
+        _check(lib().memvul_embed_layernorm(ctypes.byref(w.c), token_ids.data_ptr(), _ptr(type_ids), _ptr(lens),
+                                            _ptr(row_start), B, S, x32.data_ptr(), x16.data_ptr(), _ptr(bad),
+                                            _stream(token_ids)))
     return x32, x16
 
 

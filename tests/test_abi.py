@@ -32,11 +32,11 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
 
 def test_argument_validation_without_gpu(native_lib):
     L = native_lib
-    assert L.memvul_abi_version() == 1
+    assert L.memvul_abi_version() == 2
     assert L.memvul_gemm_f16(None, None, None, None, None, 128, 100, 64, 0, None) == -1
     assert b"N % 128" in L.memvul_last_error()
     assert L.memvul_gemm_f16(None, None, None, None, None, 128, 128, 60, 0, None) == -1
-    assert L.memvul_attention_f16(None, None, None, 1, 128, 768, None) == -1
+    assert L.memvul_attention_f16(None, None, None, None, 1, 128, 768, None) == -1
     assert L.memvul_pool_match(None, 0, None, None, None, None, None, None, None, 4, 0, 768, 512, 0,
                                None, None, None, None, None, None, None, None, 31, None) == -1
     assert b"non-empty bank" in L.memvul_last_error()
@@ -54,7 +54,9 @@ def test_workspace_size_formula(native_lib):
     M, H, I = 4 * 128, 128, 512
     up = lambda x: (x + 1023) // 1024 * 1024
     tail = up(4 * H * 4) + up(4 * H * 2) + up(4 * H * 2) + up(4 * I * 2)        # [B,*] rows of the CLS-only last layer
-    assert w.workspace_bytes(4, 128) == up(M * H * 2) + up(M * 3 * H * 2) + up(M * H * 2) + up(M * I * 2) + tail
+    base = up(M * H * 2) + up(M * 3 * H * 2) + up(M * H * 2) + up(M * I * 2) + tail
+    assert w.workspace_bytes(4, 128) == base and w.workspace_bytes(4, 128, native.ENC_PACKED | native.ENC_CLS_ONLY) == base
+    assert w.workspace_bytes(4, 128, native.ENC_PACKED) == base + up(M * H * 4)     # packed residual stream to unpack
     assert w.hidden == 128 and w.layers == 2 and w.heads == 2 and w.intermediate == 512
 
 

@@ -50,16 +50,13 @@ def test_model_memory_matches_golden(name):
     assert float((dev["logits"].cpu() - torch.from_numpy(z["logits"])).abs().max()) < TOL
     p = np.asarray(out["probs"].tolist(), dtype=np.float32)
     assert p.shape == z["p"].shape and np.abs(p - z["p"]).max() < TOL
-    # arg-max anchor identical wherever the oracle's top-2 gap exceeds the tolerance; report the margin
-    ps = z["p"][:, :, same]
-    top2 = np.sort(ps, axis=1)[:, -2:] if ps.shape[1] > 1 else np.stack([ps[:, 0] - 1, ps[:, 0]], 1)
-    clear = (top2[:, 1] - top2[:, 0]) > 2 * TOL
-    got = np.asarray(out["native"]["best_idx"].tolist())
-    assert (got[clear] == z["best_idx"][clear]).all(), (got, z["best_idx"], top2)
-    for thres in (0.5, 0.55):
-        vote_ref, vote_got = ps.max(1), p[:, :, same].max(1)
-        safe = np.abs(vote_ref - thres) > TOL
-        assert ((vote_got >= thres) == (vote_ref >= thres))[safe].all()
+    # gates on EVERY row (memvul_b200/parity.py): labels identical outside the tolerance band, the chosen anchor is a
+    # maximiser of the golden probabilities up to the observed error, identical where the golden top-2 gap is clear
+    from memvul_b200.parity import gate_report
+    g = gate_report(dev["logits"].cpu().numpy(), p, out["native"]["best_idx"].tolist(), z["logits"], z["p"], same,
+                    thresholds=(0.5, 0.55), tol=TOL)
+    print(name, {k: g[k] for k in ("max_logit_err", "min_margin", "rows_excluded", "argmax_clear_rows", "argmax_mismatch_all")})
+    assert g["ok"] and g["label_mismatch_outside_tol"] == 0 and g["argmax_not_maximiser"] == 0, g
     rows = model.make_output_human_readable(out)
     assert len(rows) == len(lens) and set(rows[0]) == {"Issue_Url", "label", "predict"} and len(rows[0]["predict"]) == len(alens)
     json.dumps(rows)
@@ -83,22 +80,17 @@ def test_bert_base_batch_against_oracle_with_labels():
     dev = out["native"]["device"]
     err = float((dev["logits"].cpu() - ref["logits"]).abs().max())
     assert err < TOL, err
-    ps = ref["p"][:, :, model._same_idx]
-    top2 = ps.topk(2, dim=1).values
-    clear = (top2[:, 0] - top2[:, 1]) > 2 * TOL
-    got = torch.tensor(out["native"]["best_idx"].tolist())
-    assert torch.equal(got[clear], ref["best_idx"][clear])
-    vote_got = torch.tensor(out["probs"].tolist())[:, :, model._same_idx].max(1).values
-    vote_ref, _ = O.vote_labels(ps, 0.5)
-    safe = (vote_ref - 0.5).abs() > TOL
-    assert torch.equal((vote_got >= 0.5)[safe], (vote_ref >= 0.5)[safe])
-    print(f"logits max err {err:.2e}; min vote margin {float((vote_ref - 0.5).abs().min()):.3e}; clear argmax rows {int(clear.sum())}/8")
+    from memvul_b200.parity import gate_report
+    g = gate_report(dev["logits"].cpu().numpy(), np.asarray(out["probs"].tolist()), out["native"]["best_idx"].tolist(),
+                    ref["logits"].numpy(), ref["p"].numpy(), model._same_idx, thresholds=(0.5,), tol=TOL)
+    print(f"logits max err {err:.2e}; gates {g}")
+    assert g["ok"] and g["rows_excluded"] == 0 and g["labels"]["0.5"]["mismatch_rows"] == 0, g
     m = model.get_metrics(reset=True)
     assert 0.0 <= m["accuracy"] <= 1.0 and "s_thres" in m and "same_f1-score" in m
 
 
 def test_full_size_properties_c2():
-    """BASELINE configs[1] size (bert-base, S=512, B=64, G=129): size-independent properties + an oracle spot check."""
+    """BASELINE configs[1] size (bert-base, S=512, B=64, G=129): size-independent properties."""
     from memvul_b200.synthetic import BERT_BASE, build_memory_model, synthetic_ids
     from oracle import memvul_oracle as O
     model, sd = build_memory_model(BERT_BASE, device="cuda")
@@ -126,11 +118,7 @@ def test_full_size_properties_c2():
             ra = model.match_batch(_dev(ids[short].contiguous(), mask[short].contiguous()))["logits"].clone()
             rb = model.match_batch(_dev(ids[short][:, :S2].contiguous(), mask[short][:, :S2].contiguous()))["logits"]
             assert float((ra - rb).abs().max()) < 1e-5
-        # oracle spot check on 3 of the 64 full-size rows
-        pick = [0, 7, 33]
-        bank = model._golden_instances_embeddings.cpu()
-        ref = O.memory_forward(sd, ids[pick], mask[pick], tids[pick], bank, model._same_idx)
-    assert float((l1[pick].cpu() - ref["logits"]).abs().max()) < TOL
+    # (all 64 rows are compared with the oracle in tests/test_configs_gpu.py::test_c2_all_64_rows_against_the_oracle)
 
 
 def test_embedder_interface_and_errors():
@@ -342,10 +330,10 @@ def test_cuda_path_matches_the_reference_run(name, tmp_path):
     print(name, {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
     ps = z["p"][:, :, same]
-    srt = np.sort(ps, axis=1)
-    clear = (srt[:, -1] - srt[:, -2]) > 2 * TOL if G > 1 else np.ones(len(ps), bool)
-    got_idx = np.asarray(out["native"]["best_idx"].tolist())
-    assert (got_idx[clear] == ps.argmax(1)[clear]).all()
+    from memvul_b200.parity import gate_report
+    gr = gate_report(dev["logits"].cpu().numpy(), p, out["native"]["best_idx"].tolist(), z["logits"], z["p"], same,
+                     thresholds=(0.5,), tol=TOL)
+    assert gr["ok"] and gr["argmax_not_maximiser"] == 0 and gr["label_mismatch_outside_tol"] == 0, gr
     rows = model.make_output_human_readable(out)
     for g, w in zip(rows, j["rows"]):
         assert g["Issue_Url"] == w["Issue_Url"] and g["label"] == w["label"] and set(g["predict"]) == set(w["predict"])
