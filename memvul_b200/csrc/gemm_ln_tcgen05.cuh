@@ -41,8 +41,14 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                            const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x32,
                            const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast,
-                           const int* __restrict__ m_dev) {
+                           const int* __restrict__ m_dev, unsigned long long* __restrict__ trace,
+                           float* __restrict__ x32_ptr, __half* __restrict__ x16_ptr) {
   using Cfg = GemmLnCfg;
+  // debug only (MEMVUL_LN_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 8 tiles
+  // (epilogue warp 0 slots 0-13, MMA warp slots 14-15; tools/ln_trace.py)
+  auto stamp = [&](uint32_t it, int k) {
+    if (trace != nullptr && blockIdx.x == 0 && it < 8u) trace[it * 16 + k] = static_cast<unsigned long long>(clock64());
+  };
   if (m_dev) M = min(M, __ldg(m_dev));     // packed (var-len) batches: the row count lives on the device
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -61,6 +67,12 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   const uint32_t leader_rank = cta_rank & ~1u;
   const bool leader = half_m == 0;
   const int idle_tma = (a_multicast >> 4) & 3, idle_mma = (a_multicast >> 6) & 3, idle_epi = (a_multicast >> 8) & 3;   // mbar_wait_idle modes of the single-lane warps
+  // epilogue variants (r02b phase trace: of a 21 k-cycle tile period at K=768, 7 k were exposed residual-load latency,
+  // 5 k the fence + remote-arrive publish round, 6 k the staging buffers waiting for their TMA stores to drain):
+  const bool direct_st = (a_multicast & 2) != 0;    // pass 2 writes x32 / x16 with 256-bit per-lane global stores: no staging, the
+                                                    // residual buffers are free after pass 1 and the NEXT tile's first two chunks are requested then
+  const bool async_stats = (a_multicast & 4) != 0;  // row statistics travel by st.async + complete_tx (no fence / arrive round)
+  const bool l2_prefetch = (a_multicast & 8) != 0;  // residual chunks 2, 3 of the next tile are pulled into L2 one tile ahead
   a_multicast &= 1;
 
   if (warp_idx == 0 && lane == 0) {
@@ -72,7 +84,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], a_multicast ? Cfg::PAIRS : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], Cfg::PAIRS * Cfg::EPI_WARPS);     // 3 CTAs x 8 warps
+    // classic exchange: 3 CTAs x 8 warps arrive; st.async exchange: one local expect_tx arrival + 6,144 bytes of complete_tx
+    for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], async_stats ? 1 : Cfg::PAIRS * Cfg::EPI_WARPS);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -135,6 +148,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait_idle(&tempty_bar[acc], acc_phase ^ 1u, idle_mma);
         tc_fence_after();
+        if (issuer) stamp(static_cast<uint32_t>((tile - cluster_id) / num_clusters), 14);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&full_bar[stage], phase, idle_mma);
@@ -152,6 +166,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         if (issuer) umma_commit_pair(&tfull_bar[acc], pair_mask);
+        if (issuer) stamp(static_cast<uint32_t>((tile - cluster_id) / num_clusters), 15);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -189,8 +204,19 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     uint32_t acc_phase = 0, gc = 0, it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int row0 = strip_row0(tile);
+      const bool tr = ew == 0 && lane == 0;
+      if (tr) stamp(it, 0);
       mbar_wait_idle(&tfull_bar[acc], acc_phase, idle_epi);
       tc_fence_after();
+      if (tr) stamp(it, 1);
+      if (l2_prefetch && !direct_st && lane == 0 && tile + num_clusters < num_tiles) {
+        // staged epilogue: the residual buffers double as the TMA-store staging of pass 2, so the next tile's residual
+        // can only be requested at the very end of this tile -- pull it into L2 now, a whole tile ahead, so that those
+        // requests (and the chunk 2 / 3 requests inside pass 1) find it there (r02b trace: 3.6 k + 3.7 k cycles of
+        // exposed HBM latency per tile -> L2 latency)
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) tma_prefetch_l2_2d(&tmap_res, col0 + c * 32, strip_row0(tile + num_clusters));
+      }
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               static_cast<uint32_t>(acc * Cfg::BN + half_sel * 128);
       // ---------------- pass 1: v = acc + bias + resid -> TMEM, row statistics ----------------
@@ -205,6 +231,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         uint8_t* rowp = ((c & 1) ? buf1 : buf0) + lane * 128;
         mbar_wait_idle(&my_res_bar[c & 1], (gc >> 1) & 1u, idle_epi);
         ++gc;
+        if (tr) stamp(it, 2 + c);
         uint32_t v[32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -224,20 +251,43 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         if (lane == 0 && c + 2 < NCHUNK) issue_res(tile, c + 2);
       }
       // ---------------- exchange the row statistics with the two other column blocks ----------------
+      if (tr) stamp(it, 6);
       const uint32_t slot = it & 1u;
+      const int next_tile = tile + num_clusters;
+      if (direct_st && lane == 0 && next_tile < num_tiles) {
+        // both residual buffers are free (pass 2 does not stage): request the next tile's first two chunks now, a whole
+        // exchange + pass 2 ahead of their use, and pull its last two chunks into L2
+        issue_res(next_tile, 0);
+        issue_res(next_tile, 1);
+        if (l2_prefetch) {
+          tma_prefetch_l2_2d(&tmap_res, col0 + 2 * 32, strip_row0(next_tile));
+          tma_prefetch_l2_2d(&tmap_res, col0 + 3 * 32, strip_row0(next_tile));
+        }
+      }
       {
         const uint32_t off = ((slot * 6u + my_src) * 128u + static_cast<uint32_t>(row_in_cta)) * 8u;
+        if (async_stats) {
+          if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&stats_bar[slot], 6u * 128u * 8u);   // what this CTA will receive
+          const uint32_t bar_local = smem_u32(&stats_bar[slot]);
 #pragma unroll
-        for (uint32_t pp = 0; pp < 3; ++pp) st_cluster_f32x2(mapa_u32(stats_base + off, pp * 2 + half_m), s1, s2);
-        fence_acq_rel_cluster();
-        __syncwarp();
-        if (lane == 0) {
+          for (uint32_t pp = 0; pp < 3; ++pp)
+            st_async_f32x2(mapa_u32(stats_base + off, pp * 2 + half_m), s1, s2, mapa_u32(bar_local, pp * 2 + half_m));
+        } else {
 #pragma unroll
-          for (uint32_t pp = 0; pp < 3; ++pp) mbar_arrive_release_cluster(&stats_bar[slot], pp * 2 + half_m);
+          for (uint32_t pp = 0; pp < 3; ++pp) st_cluster_f32x2(mapa_u32(stats_base + off, pp * 2 + half_m), s1, s2);
+          fence_acq_rel_cluster();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (uint32_t pp = 0; pp < 3; ++pp) mbar_arrive_release_cluster(&stats_bar[slot], pp * 2 + half_m);
+          }
         }
       }
       tmem_wait_st();
-      mbar_wait_cluster(&stats_bar[slot], (it >> 1) & 1u);
+      if (tr) stamp(it, 7);
+      if (async_stats) mbar_wait(&stats_bar[slot], (it >> 1) & 1u);
+      else mbar_wait_cluster(&stats_bar[slot], (it >> 1) & 1u);
+      if (tr) stamp(it, 8);
       float S1 = 0.f, S2 = 0.f;
       {
         const float2* st = reinterpret_cast<const float2*>(smem + Cfg::OFF_STATS) + (slot * 6) * 128 + row_in_cta;
@@ -254,6 +304,34 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         tmem_wait_ld();
         if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&a)[32] = r[c & 1];
+        if (direct_st) {
+          // registers -> global: every lane owns one output row; 128 B of fp32 (4 x 256-bit stores) and 64 B of fp16 (2)
+          const int grow = row0 + lane;
+          uint32_t o32[32], o16[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 g = *reinterpret_cast<const float4*>(prm + 128 + c * 32 + 4 * u);
+            const float4 be = *reinterpret_cast<const float4*>(prm + 256 + c * 32 + 4 * u);
+            const float ox = (__uint_as_float(a[4 * u + 0]) - mean) * rstd * g.x + be.x;
+            const float oy = (__uint_as_float(a[4 * u + 1]) - mean) * rstd * g.y + be.y;
+            const float oz = (__uint_as_float(a[4 * u + 2]) - mean) * rstd * g.z + be.z;
+            const float ow = (__uint_as_float(a[4 * u + 3]) - mean) * rstd * g.w + be.w;
+            o32[4 * u + 0] = __float_as_uint(ox); o32[4 * u + 1] = __float_as_uint(oy);
+            o32[4 * u + 2] = __float_as_uint(oz); o32[4 * u + 3] = __float_as_uint(ow);
+            o16[2 * u + 0] = pack_half2(ox, oy);
+            o16[2 * u + 1] = pack_half2(oz, ow);
+          }
+          if (grow < M) {
+            float* p32 = x32_ptr + static_cast<size_t>(grow) * Cfg::N + col0 + c * 32;
+            __half* p16 = x16_ptr + static_cast<size_t>(grow) * Cfg::N + col0 + c * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_global_v8(p32 + 8 * q, *reinterpret_cast<const uint32_t(*)[8]>(&o32[8 * q]));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) st_global_v8(p16 + 16 * q, *reinterpret_cast<const uint32_t(*)[8]>(&o16[8 * q]));
+          }
+          if (tr) stamp(it, 9 + c);
+          continue;
+        }
         if (lane == 0 && c > 0) bulk_wait_read_all();      // previous boxes have left buf0 (and buf1 when c is even)
         __syncwarp();
 #pragma unroll
@@ -280,15 +358,18 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           if (c & 1) tma_store_2d(&tmap_x16, buf1, col0 + (c >> 1) * 64, row0);
           bulk_commit_group();
         }
+        if (tr) stamp(it, 9 + c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(&tempty_bar[acc], leader_rank);          // accumulator stage is free again
-        bulk_wait_read_all();                                        // staging buffers are free again
-        const int nt = tile + num_clusters;
-        if (nt < num_tiles) { issue_res(nt, 0); issue_res(nt, 1); }
+        if (!direct_st) {
+          bulk_wait_read_all();                                      // staging buffers are free again
+          if (next_tile < num_tiles) { issue_res(next_tile, 0); issue_res(next_tile, 1); }
+        }
       }
+      if (tr) stamp(it, 13);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

@@ -22,6 +22,10 @@
 
 namespace mv {
 
+#ifndef MV_GELU_PACKED
+#define MV_GELU_PACKED 1        // erf-GELU epilogue on fp32 pairs (FFMA2 / FMUL2): fewer issue slots per element
+#endif
+
 template <int EPI>
 struct Gemm2Cfg {
   static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
@@ -263,8 +267,13 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
               x[6] = __uint_as_float(v[8 * u + 6]) + b1.z;
               x[7] = __uint_as_float(v[8 * u + 7]) + b1.w;
               if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#if MV_GELU_PACKED
+#pragma unroll
+                for (int t = 0; t < 8; t += 2) gelu_erf_fast_x2(x[t], x[t + 1]);
+#else
 #pragma unroll
                 for (int t = 0; t < 8; ++t) x[t] = gelu_erf_fast(x[t]);
+#endif
               }
               pkd[4 * u + 0] = pack_half2(x[0], x[1]);
               pkd[4 * u + 1] = pack_half2(x[2], x[3]);

@@ -14,6 +14,7 @@
 
 #include "../../include/memvul_b200.h"
 #include "attention_tcgen05.cuh"
+#include "attention_tcgen05_v2.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "gemm_ln_tcgen05.cuh"
@@ -348,6 +349,12 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   // TMA multicast of A across the three pairs works but measured 2-4 % slower than unicast (the main loop is not
   // L2-bound: DESIGN.md section 3), so it is opt-in: MEMVUL_LN_MULTICAST=1.
   static const bool a_mc = [] { const char* e = getenv("MEMVUL_LN_MULTICAST"); return e && strcmp(e, "1") == 0; }();
+  // MEMVUL_LN_MODE: epilogue variant bits (1 direct global stores + early residual request, 2 st.async statistics
+  // exchange, 4 L2 prefetch of the next tile's residual); default 2: r02c/r02d measured 83 -> 74 us at K=768 for the
+  // st.async exchange alone; direct row-strided stores cost 3 k cycles per chunk against 1.4 k for the staged TMA
+  // stores, and the L2 prefetch does not shorten the residual wait (the TMA queue under load, not HBM, is the
+  // latency); 0 = the r01 epilogue
+  static const int ln_mode = [] { const char* e = getenv("MEMVUL_LN_MODE"); return e ? atoi(e) & 7 : 2; }();
   CUtensorMap ta, ta64, tb, tres, t32, t16;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 64, &ta64)) return rc;
@@ -357,9 +364,22 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   if (int rc = make_map(x16, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2, &t16)) return rc;
   const int tiles = (M + Cfg::BM - 1) / Cfg::BM;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  LaunchScope ls(g_cls, st);
-  kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (gemm_wait_mode() << 4), m_dev);
-  CUDA_TRY(cudaGetLastError());
+  // MEMVUL_LN_TRACE=<file>: debug only -- CTA 0 records clock64() per epilogue / MMA phase (tools/ln_trace.py)
+  static const char* trace_path = getenv("MEMVUL_LN_TRACE");
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_path && !trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 128 * 8));
+  if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 128 * 8, st));
+  {
+    LaunchScope ls(g_cls, st);
+    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16));
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
+    std::vector<unsigned long long> host(128);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(host.data(), trace_buf, 128 * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, 128, f); fclose(f); }
+  }
   return MEMVUL_OK;
 }
 
@@ -380,7 +400,13 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, &tq)) return rc;
   if (int rc = make_map_f16(qkv, (uint64_t)B * S, (uint64_t)3 * H, (uint64_t)3 * H, mv::AttnCfg::BKV, &tkv)) return rc;
   if (int rc = make_map_f16(ctx, (uint64_t)B * S, (uint64_t)H, (uint64_t)H, 32, &tctx)) return rc;   // ctx write-out boxes
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc;
+  // MEMVUL_ATT_V=2 selects the experimental second-generation kernel (attention_tcgen05_v2.cuh: 8 soft-max warps splitting
+  // every row, separate Q K^T / P V issuers, double-buffered O).  It is parity-green but measured SLOWER (r02e: 133.7 us
+  // against 116.3 us at 64 x 512): the block period is set by the MUFU phase all warps of a CTA enter together, not by
+  // the per-thread chain that the split shortens.  Default: the first-generation kernel.
+  static const bool v1 = [] { const char* e = getenv("MEMVUL_ATT_V"); return !(e && atoi(e) == 2); }();
+  if (v1) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc; }
+  else { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
   const int n_items = B * (H / 64) * n_qt;
   const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
@@ -391,10 +417,16 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
     CUDA_TRY(cudaMalloc(&trace_buf, 2048 * 8));
   }
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 2048 * 8, st));
-  LaunchScope ls(first_tile_only ? KC_ATTENTION_CLS : KC_ATTENTION, st);
-  mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
-      tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
-  CUDA_TRY(cudaGetLastError());
+  {
+    LaunchScope ls(first_tile_only ? KC_ATTENTION_CLS : KC_ATTENTION, st);
+    if (v1)
+      mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+    else
+      mv::attention_tcgen05_v2_kernel<<<grid, mv::Attn2Cfg::THREADS, mv::Attn2Cfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+    CUDA_TRY(cudaGetLastError());
+  }
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
     std::vector<unsigned long long> host(2048);
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -18,7 +18,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmemvul_b200.so")
-SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh", "rowwise.cuh", "pool_match.cuh"]
+SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh",
+           "attention_tcgen05_v2.cuh", "rowwise.cuh", "pool_match.cuh"]
 
 ABI_VERSION = 2
 EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32 = 0, 1, 2
