@@ -3,4 +3,4 @@
 Importing it registers the B200-native implementations under the reference's names."""
 from memvul_b200 import *  # noqa: F401,F403
 from memvul_b200 import (ModelMemory, ModelSingle, PretrainedTransformerEmbedder, ReaderMemory,  # noqa: F401
-                         SiameseMeasureV1)
+                         ReaderSingle, SiameseMeasureV1)

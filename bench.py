@@ -347,6 +347,8 @@ def run_native(args):
     ids_d, mask_d, tids_d = ids_h.to(dev), mask_h.to(dev), tids_h.to(dev)
     sample_d = {"tokens": {"token_ids": ids_d, "mask": mask_d, "type_ids": tids_d}}
     gather = AsyncGather(counts, dev) if world > 1 else None
+    if gather is not None:
+        model.shard_capacity = max(counts)           # results in one flat buffer: the all-gather needs no packing
 
     def step_resident():
         res = model.match_batch(sample_d)

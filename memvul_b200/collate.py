@@ -14,11 +14,14 @@ import torch
 
 
 def collate_instances(instances: List[Dict[str, Any]], device: Optional[torch.device] = None,
-                      pad_to: Optional[int] = None) -> Dict[str, Any]:
+                      pad_to: Optional[int] = None, key: str = "sample1", host_only: bool = False) -> Dict[str, Any]:
+    """``key``: the text field's name -- ``sample1`` for reader_memory instances, ``sample`` for reader_single ones.
+    ``host_only``: build the (pinned) host tensors but leave the copy to the caller (``batch_to_device``): what a
+    prefetch thread does."""
     B = len(instances)
     if B == 0:
         raise ValueError("cannot collate an empty batch")
-    lens = [len(i["sample1"]["token_ids"]) for i in instances]
+    lens = [len(i[key]["token_ids"]) for i in instances]
     if min(lens) == 0:
         raise ValueError("instance with zero tokens")
     S = max(lens) if pad_to is None else max(pad_to, max(lens))
@@ -27,21 +30,32 @@ def collate_instances(instances: List[Dict[str, Any]], device: Optional[torch.de
     tids = torch.zeros(B, S, dtype=torch.int64, pin_memory=pin)
     mask = torch.zeros(B, S, dtype=torch.bool, pin_memory=pin)
     for b, inst in enumerate(instances):
-        t = inst["sample1"]
+        t = inst[key]
         n = lens[b]
         ids[b, :n] = torch.as_tensor(t["token_ids"], dtype=torch.int64)
         if t.get("type_ids") is not None:
             tids[b, :n] = torch.as_tensor(t["type_ids"], dtype=torch.int64)
         mask[b, :n] = True
     batch: Dict[str, Any] = {}
-    if device is not None:
+    if device is not None and not host_only:
         ids, tids, mask = (x.to(device, non_blocking=True) for x in (ids, tids, mask))
-    batch["sample1"] = {"tokens": {"token_ids": ids, "mask": mask, "type_ids": tids}}
+    batch[key] = {"tokens": {"token_ids": ids, "mask": mask, "type_ids": tids}}
     if all(i.get("label") is not None for i in instances):
         lab = torch.tensor([int(i["label"]) for i in instances], dtype=torch.int64)
-        batch["label"] = lab.to(device, non_blocking=True) if device is not None else lab
+        if pin:
+            lab = lab.pin_memory()
+        batch["label"] = lab.to(device, non_blocking=True) if device is not None and not host_only else lab
     batch["metadata"] = [i["metadata"] for i in instances]
     return batch
+
+
+def batch_to_device(batch: Dict[str, Any], device: torch.device, key: str = "sample1") -> Dict[str, Any]:
+    """Asynchronous H2D of a ``host_only`` batch on the caller's current stream."""
+    out = dict(batch)
+    out[key] = {"tokens": {k: v.to(device, non_blocking=True) for k, v in batch[key]["tokens"].items()}}
+    if "label" in batch:
+        out["label"] = batch["label"].to(device, non_blocking=True)
+    return out
 
 
 def batches(instances: List[Dict[str, Any]], batch_size: int):

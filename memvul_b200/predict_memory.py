@@ -82,48 +82,89 @@ def build_memory(model, golden_instances: List[Dict[str, Any]], chunk: int = 128
         model.forward_on_instances(golden_instances[chunk:])
 
 
+def _prefetched(instances: Iterable[Dict[str, Any]], batch_size: int, device: torch.device, depth: int = 3):
+    """Data-order batches built by a background thread: the reader's lazy tokenisation (Rust, GIL released) and the
+    pinned-memory collation of batch i+1.. run while the main thread keeps the GPU fed with batch i.  Yields
+    (host batch, instance count); exceptions of the producer are re-raised in the consumer."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    END = object()
+
+    def produce():
+        try:
+            chunk: List[Dict[str, Any]] = []
+            for inst in instances:
+                chunk.append(inst)
+                if len(chunk) == batch_size:
+                    q.put((collate_instances(chunk, device, host_only=True), len(chunk)))
+                    chunk = []
+            if chunk:
+                q.put((collate_instances(chunk, device, host_only=True), len(chunk)))
+            q.put(END)
+        except BaseException as e:          # noqa: BLE001 -- handed to the consumer
+            q.put(e)
+    threading.Thread(target=produce, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is END:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 def evaluate(model, instances: Iterable[Dict[str, Any]], batch_size: int, device: torch.device,
              predictions_output_file: Optional[str] = None, output_file: Optional[str] = None,
              bucket_by_length: bool = False) -> Dict[str, Any]:
     """AllenNLP ``evaluate`` for this model: forward every batch under no_grad, write readable predictions (one JSON
-    array per ``batch_size`` instances per line, in data order).  ``bucket_by_length`` groups instances of similar
-    length into the same batch (collate.plan_length_buckets) and restores data order on output; padded tokens cost
-    full price, so this is worth ~2x on a {128,256,512} mix while the written file is identical."""
-    from .collate import plan_length_buckets
-    instances = list(instances)
-    n = len(instances)
-    if bucket_by_length:
-        plan = plan_length_buckets([len(i["sample1"]["token_ids"]) for i in instances], batch_size)
-    else:
-        plan = [list(range(i, min(n, i + batch_size))) for i in range(0, n, batch_size)]
-    rows: List[Any] = [None] * n
+    array per ``batch_size`` instances per line, in data order).  Data order (default): instances are consumed as a
+    stream through a prefetch thread, padded tokens cost nothing (packed execution).  ``bucket_by_length`` groups
+    instances of similar length into the same batch (collate.plan_length_buckets) and restores data order on output; it
+    needs the whole data set up front and only matters for the padded execution (MEMVUL_ENC_PACKED=0)."""
+    from .collate import batch_to_device, plan_length_buckets
     pred_f = open(predictions_output_file, "w", encoding="utf-8") if predictions_output_file else None
-    written = 0
+    if not bucket_by_length:
+        prev = None
+        with torch.no_grad():
+            for host_batch, _ in _prefetched(instances, batch_size, device):
+                out = model(**batch_to_device(host_batch, device))
+                if prev is not None and pred_f is not None:   # batch i-1's host work overlaps batch i's kernels
+                    pred_f.write(json.dumps(model.make_output_human_readable(prev)) + "\n")
+                prev = out
+            if prev is not None and pred_f is not None:
+                pred_f.write(json.dumps(model.make_output_human_readable(prev)) + "\n")
+    else:
+        instances = list(instances)
+        n = len(instances)
+        plan = plan_length_buckets([len(i["sample1"]["token_ids"]) for i in instances], batch_size)
+        rows: List[Any] = [None] * n
+        written = 0
 
-    def drain(out, idx):
-        nonlocal written
-        if pred_f is None:
-            return
-        for i, row in zip(idx, model.make_output_human_readable(out)):
-            rows[i] = row
-        while written < n:                                    # emit every complete data-order line
-            hi = min(n, written + batch_size)
-            if any(rows[i] is None for i in range(written, hi)):
-                break
-            pred_f.write(json.dumps(rows[written:hi]) + "\n")
-            for i in range(written, hi):
-                rows[i] = True
-            written = hi
-    prev = None
-    with torch.no_grad():
-        for idx in plan:
-            batch = collate_instances([instances[i] for i in idx], device)
-            out = model(**batch)
-            if prev is not None:                                # batch i-1's host work overlaps batch i's kernels
+        def drain(out, idx):
+            nonlocal written
+            if pred_f is None:
+                return
+            for i, row in zip(idx, model.make_output_human_readable(out)):
+                rows[i] = row
+            while written < n:                                    # emit every complete data-order line
+                hi = min(n, written + batch_size)
+                if any(rows[i] is None for i in range(written, hi)):
+                    break
+                pred_f.write(json.dumps(rows[written:hi]) + "\n")
+                for i in range(written, hi):
+                    rows[i] = True
+                written = hi
+        prev = None
+        with torch.no_grad():
+            for idx in plan:
+                batch = collate_instances([instances[i] for i in idx], device)
+                out = model(**batch)
+                if prev is not None:
+                    drain(*prev)
+                prev = (out, idx)
+            if prev is not None:
                 drain(*prev)
-            prev = (out, idx)
-        if prev is not None:
-            drain(*prev)
     if pred_f:
         pred_f.close()
     metrics = model.get_metrics(reset=True)

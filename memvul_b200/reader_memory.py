@@ -54,19 +54,20 @@ class ReaderMemory(DatasetReader):
         self._label_vocab = {t: vocab.get_token_index(t, namespace) for t in ("same", "diff")}
 
     # ------------------------------------------------------------------ reading
-    def read_dataset(self, file_path: str) -> Dict[str, list]:
-        if "golden" in file_path:
-            with open(file_path, encoding="utf-8") as f:
-                anchors = json.load(f)
-            return {cwe: [{self._target: cwe, "description": self._tokenizer.tokenize(desc)}]
-                    for cwe, desc in anchors.items()}
-        if file_path in self._dataset:
-            return self._dataset[file_path]
+    TOKENIZE_CHUNK = 512      # texts per tokenize_batch call: the Rust backend encodes a chunk on all cores, GIL released
+
+    def _tokenize_all(self, texts: List[str]) -> List[List[str]]:
+        if hasattr(self._tokenizer, "tokenize_batch"):
+            return self._tokenizer.tokenize_batch(texts)
+        return [self._tokenizer.tokenize(t) for t in texts]
+
+    def _group(self, file_path: str) -> Dict[str, list]:
+        """reader_memory.py:82-111 without the tokenisation: label every sample, key positives by the CWE id of their
+        CVE, drop positives whose CWE id is None.  Groups keep first-seen order (``neg`` first, :84)."""
         with open(file_path, encoding="utf-8") as f:
             samples = json.load(f)
         dataset: Dict[str, list] = {"neg": []}
         for s in samples:
-            s["description"] = self._tokenizer.tokenize(f"{s['Issue_Title']}. {s['Issue_Body']}")
             label = "pos" if str(s[self._target]) == "1" else "neg"
             s[self._target] = label
             if label == "pos":
@@ -76,26 +77,48 @@ class ReaderMemory(DatasetReader):
                     continue
                 dataset.setdefault(label, [])
             dataset[label].append(s)
+        return dataset
+
+    def read_dataset(self, file_path: str) -> Dict[str, list]:
+        if "golden" in file_path:
+            with open(file_path, encoding="utf-8") as f:
+                anchors = json.load(f)
+            toks = self._tokenize_all(list(anchors.values()))
+            return {cwe: [{self._target: cwe, "description": t}] for cwe, t in zip(anchors, toks)}
+        if file_path in self._dataset:
+            return self._dataset[file_path]
+        dataset = self._group(file_path)
+        flat = [s for group in dataset.values() for s in group]
+        for s, t in zip(flat, self._tokenize_all([f"{s['Issue_Title']}. {s['Issue_Body']}" for s in flat])):
+            s["description"] = t
         self._dataset[file_path] = dataset
         return dataset
 
     def _read(self, file_path: str) -> Iterator[Dict[str, Any]]:
-        dataset = self.read_dataset(file_path)
-        all_data: List[dict] = []
-        for group in dataset.values():
-            all_data.extend(group)
         if "golden_" in file_path:
-            for sample in all_data:
-                yield self.text_to_instance((sample, sample), type_="golden")
-        elif "test_" in file_path:
-            for sample in reversed(all_data):
-                yield self.text_to_instance((sample, sample), type_="unlabel")
+            for group in self.read_dataset(file_path).values():
+                for sample in group:
+                    yield self.text_to_instance((sample, sample), type_="golden")
+            return
+        if "test_" in file_path:
+            type_ = "unlabel"
         elif "validation_" in file_path:
-            for sample in reversed(all_data):
-                yield self.text_to_instance((sample, sample), type_="test")
+            type_ = "test"
         else:
             raise NotImplementedError("training-pair sampling (reader_memory.py:164-192) is out of scope for "
                                       "memvul_b200; file names must contain golden_, test_ or validation_")
+        # Evaluation streams are emitted in REVERSED concatenation order (:150,158) and tokenised lazily, chunk by chunk,
+        # so that a consumer (predict_memory.evaluate's prefetch thread) overlaps tokenisation with the GPU.
+        dataset = self._dataset.get(file_path) or self._group(file_path)
+        order = [s for group in dataset.values() for s in group][::-1]
+        for c0 in range(0, len(order), self.TOKENIZE_CHUNK):
+            chunk = order[c0:c0 + self.TOKENIZE_CHUNK]
+            todo = [s for s in chunk if "description" not in s]
+            for s, t in zip(todo, self._tokenize_all([f"{s['Issue_Title']}. {s['Issue_Body']}" for s in todo])):
+                s["description"] = t
+            for sample in chunk:
+                yield self.text_to_instance((sample, sample), type_=type_)
+        self._dataset[file_path] = dataset
 
     def text_to_instance(self, p, type_: str = "train") -> Dict[str, Any]:
         ins1, _ = p

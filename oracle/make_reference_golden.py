@@ -229,12 +229,46 @@ def run_reader_case(name: str = "ref_reader") -> None:
     print(name, {k: len(v) for k, v in out.items()})
 
 
+def run_reader_single_case(name: str = "ref_reader_single") -> None:
+    """MemVul/reader_single.py: __init__ (:33-51), read_dataset (:53-71), _read evaluation branches (:73-94),
+    text_to_instance (:112-126), over the same toy vocabulary / data files as ``ref_reader``."""
+    import importlib
+    from oracle import ref_shim
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from toy_vocab import TOY_VOCAB, write_toy_data
+    ref_shim.install()
+    ref_shim.import_reference(REFERENCE)
+    rs = importlib.import_module("MemVul.reader_single")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        vocab_file = os.path.join(tmp, "vocab.txt")
+        with open(vocab_file, "w") as f:
+            f.write("\n".join(TOY_VOCAB) + "\n")
+        paths = write_toy_data(tmp)
+        tok = ref_shim.PretrainedTransformerTokenizer(vocab_file, add_special_tokens=True, max_length=16)
+        reader = rs.ReaderSingle(tokenizer=tok, target="Security_Issue_Full", sample_neg=0.1,
+                                 token_indexers={"tokens": ref_shim.PretrainedTransformerIndexer(vocab_file, namespace="tags")})
+        for kind in ("test", "validation"):
+            rows = []
+            for inst in reader.read(paths[kind]):
+                f = inst.fields
+                idx = f["sample"]._token_indexers["tokens"].tokens_to_indices(f["sample"].tokens)
+                rows.append({"tokens": [t.text for t in f["sample"].tokens], "token_ids": idx["token_ids"],
+                             "type_ids": idx["type_ids"], "label": f["label"].label, "metadata": f["metadata"].metadata})
+            out[kind] = rows
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump({"instances": out, "reference_files": ["MemVul/reader_single.py"]}, f, indent=1)
+    print(name, {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     import subprocess
-    if len(sys.argv) > 1 and sys.argv[1] == "ref_reader":
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_reader_single":
+        run_reader_single_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ref_reader":
         run_reader_case()
     elif len(sys.argv) > 1:
         (run_single_case if sys.argv[1] in SINGLE_CASES else run_case)(sys.argv[1])
     else:                           # one process per case: ref_shim.SETTINGS and the reference modules are per-process
-        for name in list(CASES) + list(SINGLE_CASES) + ["ref_reader"]:
+        for name in list(CASES) + list(SINGLE_CASES) + ["ref_reader", "ref_reader_single"]:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), name])

@@ -144,7 +144,7 @@ def test_reader_eval_branches(tmp_path_factory, vocab_file):
     gold = list(reader.read(g))
     assert [i["metadata"]["instance"][0]["label"] for i in gold] == ["CWE-79", "CWE-120", "CWE-416"]
     assert all(i["metadata"]["type"] == "golden" and i["label"] is None for i in gold)
-    assert gold[1]["sample1"]["token_ids"] == [2, 5, 6, 7, 3]          # [CLS] buffer over ##flow [SEP]
+    assert list(gold[1]["sample1"]["token_ids"]) == [2, 5, 6, 7, 3]          # [CLS] buffer over ##flow [SEP]
     test = list(reader.read(t))
     # dataset = {"neg":[u0,u2], "CWE-120":[u1], "CWE-79":[u3]} (u4 dropped: CWE id None) -> reversed concat
     assert [i["metadata"]["instance"][0]["Issue_Url"] for i in test] == ["u3", "u1", "u2", "u0"]

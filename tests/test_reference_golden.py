@@ -133,8 +133,39 @@ def test_host_reader_reproduces_the_reference_reader(tmp_path_factory):
         got = list(reader.read(paths[kind]))
         assert len(got) == len(ref[kind])
         for g, w in zip(got, ref[kind]):
-            assert g["sample1"]["token_ids"] == w["token_ids"] and g["sample1"]["type_ids"] == w["type_ids"]
+            assert list(g["sample1"]["token_ids"]) == w["token_ids"] and list(g["sample1"]["type_ids"]) == w["type_ids"]
             assert g["metadata"] == w["metadata"]
             assert g.get("label_str") == w["label"]
             if w["label"] is not None:
                 assert g["label"] == labels.get_token_index(w["label"], "labels")
+
+
+def test_host_reader_single_reproduces_the_reference_reader(tmp_path_factory):
+    """MemVul/reader_single.py executed from /root/reference over the toy files: same instances in the same order (groups
+    in first-seen label order, NOT reversed), same word pieces, labels and metadata (BASELINE configs[0] plumbing)."""
+    from memvul_b200.registrable import DatasetReader, Vocabulary
+    from toy_vocab import TOY_VOCAB, write_toy_data
+    with open(os.path.join(GOLD, "ref_reader_single.json")) as f:
+        ref = json.load(f)["instances"]
+    tmp = tmp_path_factory.mktemp("data")
+    vocab_file = os.path.join(str(tmp), "vocab.txt")
+    with open(vocab_file, "w") as f:
+        f.write("\n".join(TOY_VOCAB) + "\n")
+    paths = write_toy_data(tmp)
+    reader = DatasetReader.from_params({"type": "reader_single", "target": "Security_Issue_Full",
+                                        "tokenizer": {"type": "pretrained_transformer", "model_name": vocab_file,
+                                                      "add_special_tokens": True, "max_length": 16},
+                                        "token_indexers": {"tokens": {"type": "pretrained_transformer", "namespace": "tags"}}})
+    labels = Vocabulary({"class_labels": ["neg", "pos"]})
+    reader.index_with(labels)
+    for kind in ("test", "validation"):
+        got = list(reader.read(paths[kind]))
+        assert len(got) == len(ref[kind])
+        for g, w in zip(got, ref[kind]):
+            assert list(g["sample"]["token_ids"]) == w["token_ids"] and list(g["sample"]["type_ids"]) == w["type_ids"]
+            assert g["metadata"] == w["metadata"] and g["label_str"] == w["label"]
+            assert g["label"] == labels.get_token_index(w["label"], "class_labels")
+    import shutil
+    shutil.copy(paths["test"], os.path.join(str(tmp), "train_project.json"))
+    with pytest.raises(NotImplementedError):            # the sampled training stream is out of scope
+        list(reader.read(os.path.join(str(tmp), "train_project.json")))
