@@ -428,10 +428,14 @@ def run_native(args):
         ms_e2e, _, _ = timed(step_e2e, steps, after=drain)
         model.get_metrics(reset=True)
 
-        # live per-kernel timing: same step with CUDA events around every launch
+        # live per-kernel timing: same step with CUDA events around every launch, right after ~1 s of un-instrumented
+        # steps so that the table is taken in the same sustained clock regime as `value` (r02c: profiled cold, FFN-up
+        # showed 1.00 of the SUSTAINED peak)
+        for _ in range(max(3, preheat_steps // 3)):
+            model.match_batch(sample_d)
         native.profile_enable(True)
         native.profile_read()
-        prof_steps = 3
+        prof_steps = 10
         for _ in range(prof_steps):
             model.match_batch(sample_d)
         prof = native.profile_read()

@@ -42,7 +42,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                            const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast,
                            const int* __restrict__ m_dev, unsigned long long* __restrict__ trace,
-                           float* __restrict__ x32_ptr, __half* __restrict__ x16_ptr) {
+                           float* __restrict__ x32_ptr, __half* __restrict__ x16_ptr, const float* resid_ptr) {
   using Cfg = GemmLnCfg;
   // debug only (MEMVUL_LN_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 8 tiles
   // (epilogue warp 0 slots 0-13, MMA warp slots 14-15; tools/ln_trace.py)
@@ -73,6 +73,14 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                                                     // residual buffers are free after pass 1 and the NEXT tile's first two chunks are requested then
   const bool async_stats = (a_multicast & 4) != 0;  // row statistics travel by st.async + complete_tx (no fence / arrive round)
   const bool l2_prefetch = (a_multicast & 8) != 0;  // residual chunks 2, 3 of the next tile are pulled into L2 one tile ahead
+  // depth of the A/B ring actually used (<= Cfg::STAGES).  The TMA unit serves an SM's requests in order, so the epilogue's
+  // residual boxes queue behind every main-loop stage in flight: a short-K problem (K = 768: 12 K-blocks per tile, the
+  // kernel is epilogue / HBM bound) wants a SHALLOW ring, the K = 3072 one all four stages.
+  const int nstages = ((a_multicast >> 12) & 7) ? ((a_multicast >> 12) & 7) : Cfg::STAGES;
+  // residual boxes by per-lane cp.async (LDGSTS) instead of TMA: r02h showed that a residual box requested through the TMA
+  // unit waits behind the four main-loop stages queued ahead of it (3.1 k + 4.1 k exposed cycles per tile at K = 768; 0.2 k
+  // with a 2-deep ring, which starves the MMA instead) -- the LSU path has its own queue
+  const bool res_ldgsts = ((a_multicast >> 15) & 1) != 0;
   a_multicast &= 1;
 
   if (warp_idx == 0 && lane == 0) {
@@ -83,7 +91,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     // all three pairs have retired (3 multicast commits); unicast: only this pair's.
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], a_multicast ? Cfg::PAIRS : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
-    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], res_ldgsts ? 32 : 1);   // one arrival per lane / one expect_tx
     // classic exchange: 3 CTAs x 8 warps arrive; st.async exchange: one local expect_tx arrival + 6,144 bytes of complete_tx
     for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], async_stats ? 1 : Cfg::PAIRS * Cfg::EPI_WARPS);
     fence_barrier_init();
@@ -130,7 +138,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           }
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictLast);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -163,7 +171,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                                (kb | k) != 0 ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage], a_multicast ? static_cast<uint16_t>(0b111111) : pair_mask);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         if (issuer) umma_commit_pair(&tfull_bar[acc], pair_mask);
         if (issuer) stamp(static_cast<uint32_t>((tile - cluster_id) / num_clusters), 15);
@@ -195,10 +203,25 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     auto strip_row0 = [&](int tile) { return tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA + quarter * 32; };
     auto issue_res = [&](int tile, int c) {                 // residual box (rows of `tile`, chunk c) -> buffer c & 1
       uint8_t* dst = (c & 1) ? buf1 : buf0;
-      mbar_arrive_expect_tx(&my_res_bar[c & 1], Cfg::STG_BYTES);
-      tma_load_2d(dst, &tmap_res, &my_res_bar[c & 1], col0 + c * 32, strip_row0(tile), kEvictFirst);
+      if (res_ldgsts) {
+        // whole warp: lane -> (row lane/8 + 4 i, 16-byte unit lane%8); four full 128 B lines per instruction, written to
+        // the positions a SWIZZLE_128B TMA box would use
+        const uint32_t d0 = smem_u32(dst);
+        const int unit = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (lane >> 3) + 4 * i;
+          const int grow = min(strip_row0(tile) + r, M - 1);           // rows past M repeat the last row (never stored)
+          cp_async_16B(d0 + r * 128 + ((unit ^ (r & 7)) << 4),
+                       resid_ptr + static_cast<size_t>(grow) * Cfg::N + col0 + c * 32 + unit * 4);
+        }
+        cp_async_mbar_arrive(&my_res_bar[c & 1]);
+      } else if (lane == 0) {
+        mbar_arrive_expect_tx(&my_res_bar[c & 1], Cfg::STG_BYTES);
+        tma_load_2d(dst, &tmap_res, &my_res_bar[c & 1], col0 + c * 32, strip_row0(tile), kEvictFirst);
+      }
     };
-    if (lane == 0 && cluster_id < num_tiles) { issue_res(cluster_id, 0); issue_res(cluster_id, 1); }
+    if (cluster_id < num_tiles) { issue_res(cluster_id, 0); issue_res(cluster_id, 1); }
 
     int acc = 0;
     uint32_t acc_phase = 0, gc = 0, it = 0;
@@ -248,18 +271,18 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         }
         tmem_st_32x32b_x32(t_addr + c * 32, v);            // stash for pass 2
         __syncwarp();                                      // every lane has read this residual buffer
-        if (lane == 0 && c + 2 < NCHUNK) issue_res(tile, c + 2);
+        if (c + 2 < NCHUNK) issue_res(tile, c + 2);
       }
       // ---------------- exchange the row statistics with the two other column blocks ----------------
       if (tr) stamp(it, 6);
       const uint32_t slot = it & 1u;
       const int next_tile = tile + num_clusters;
-      if (direct_st && lane == 0 && next_tile < num_tiles) {
+      if (direct_st && next_tile < num_tiles) {
         // both residual buffers are free (pass 2 does not stage): request the next tile's first two chunks now, a whole
         // exchange + pass 2 ahead of their use, and pull its last two chunks into L2
         issue_res(next_tile, 0);
         issue_res(next_tile, 1);
-        if (l2_prefetch) {
+        if (l2_prefetch && lane == 0) {
           tma_prefetch_l2_2d(&tmap_res, col0 + 2 * 32, strip_row0(next_tile));
           tma_prefetch_l2_2d(&tmap_res, col0 + 3 * 32, strip_row0(next_tile));
         }
@@ -364,10 +387,11 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(&tempty_bar[acc], leader_rank);          // accumulator stage is free again
-        if (!direct_st) {
-          bulk_wait_read_all();                                      // staging buffers are free again
-          if (next_tile < num_tiles) { issue_res(next_tile, 0); issue_res(next_tile, 1); }
-        }
+        if (!direct_st) bulk_wait_read_all();                        // staging buffers are free again
+      }
+      if (!direct_st) {
+        __syncwarp();
+        if (next_tile < num_tiles) { issue_res(next_tile, 0); issue_res(next_tile, 1); }
       }
       if (tr) stamp(it, 13);
       acc ^= 1;

@@ -22,6 +22,11 @@
 
 namespace mv {
 
+#ifndef MV_GEMM_STG2
+#define MV_GEMM_STG2 0          // 1: two staging buffers per epilogue warp for the fp16-output epilogues.  Measured r02h:
+                                // QKV 87.9 -> 90.2 us, FFN-up 124.6 -> 126.7 us, i.e. the store cost is NOT a warp waiting for
+                                // its staging buffer to drain; kept for the record
+#endif
 #ifndef MV_GELU_PACKED
 #define MV_GELU_PACKED 1        // erf-GELU epilogue on fp32 pairs (FFMA2 / FMUL2): fewer issue slots per element
 #endif
@@ -38,10 +43,17 @@ struct Gemm2Cfg {
   static constexpr int THREADS = 384;
   static constexpr int EPI_WARPS = 8;
   static constexpr int STG_BYTES = 4096;                   // 32 rows x 128 B, SWIZZLE_128B
-  static constexpr int STG_BUFS = RESID ? 2 : 1;          // RESID: ping-pong, next residual box in flight
+  // RESID: ping-pong, next residual box in flight.  fp16 outputs: ping-pong too (MV_GEMM_STG2) -- the TMA unit serves an
+  // SM's requests in order, so an output box queues behind every main-loop stage in flight (~2.5 k cycles) and a warp
+  // that must see its single staging buffer drained before packing the next box spends the epilogue waiting
+  static constexpr int STG_BUFS = (RESID || MV_GEMM_STG2) ? 2 : 1;
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;
-  static constexpr int OFF_BIAS = OFF_STG + EPI_WARPS * STG_BUFS * STG_BYTES;      // 8 warps x 128 floats
-  static constexpr int OFF_BAR = OFF_BIAS + EPI_WARPS * 128 * 4;
+  // bias slices: a private 128-float copy per epilogue warp (the warps are not in lock step across tiles).  With two
+  // fp16 staging buffers the 4 KB no longer fit next to five main-loop stages; those epilogues read the bias through
+  // the read-only cache instead (same address in every lane: one broadcast transaction)
+  static constexpr bool BIAS_SMEM = RESID || !MV_GEMM_STG2;
+  static constexpr int OFF_BIAS = OFF_STG + EPI_WARPS * STG_BUFS * STG_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + (BIAS_SMEM ? EPI_WARPS * 128 * 4 : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 512;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared-memory limit");
 };
@@ -172,7 +184,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
     const int half_sel = ew >> 2;                  // column half of the 256-wide tile
     constexpr int COLS_PER_WARP = Cfg::BN / 2;     // 128
     constexpr int NCHUNK = COLS_PER_WARP / 32;     // 4 TMEM chunks of 32 fp32 columns
-    float* my_bias = bias_smem + ew * 128;
+    float* my_bias = bias_smem + (Cfg::BIAS_SMEM ? ew * 128 : 0);
     uint8_t* my_stg = smem + Cfg::OFF_STG + ew * Cfg::STG_BUFS * Cfg::STG_BYTES;
     uint64_t* my_res_bar = res_bar + 2 * ew;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);          // 128B-swizzle phase of this lane's staging row
@@ -180,6 +192,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t gc = 0;                               // running residual-chunk counter: buffer gc & 1, parity (gc >> 1) & 1
+    uint32_t bx = 0;                               // running fp16 output-box counter: staging buffer bx & 1
 
     auto strip_row0 = [&](int tile) { return (tile / tiles_n) * Cfg::BM + static_cast<int>(cta_rank) * Cfg::BM_CTA + quarter * 32; };
     auto strip_col0 = [&](int tile) { return (tile % tiles_n) * Cfg::BN + half_sel * COLS_PER_WARP; };
@@ -203,8 +216,10 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int row0 = strip_row0(tile), col0 = strip_col0(tile);
       // bias slice of this warp -> smem (independent of the accumulator: overlaps the wait below)
-      *reinterpret_cast<float4*>(my_bias + lane * 4) = __ldg(reinterpret_cast<const float4*>(bias + col0) + lane);
-      __syncwarp();
+      if constexpr (Cfg::BIAS_SMEM) {
+        *reinterpret_cast<float4*>(my_bias + lane * 4) = __ldg(reinterpret_cast<const float4*>(bias + col0) + lane);
+        __syncwarp();
+      }
       mbar_wait_idle(&tfull_bar[acc], acc_phase, idle_epi);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -216,7 +231,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         tmem_wait_ld();
         if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&v)[32] = r[c & 1];
-        const float* bsm = my_bias + c * 32;
+        const float* bsm = Cfg::BIAS_SMEM ? my_bias + c * 32 : bias + col0 + c * 32;
         if constexpr (Cfg::RESID) {
           const uint32_t b = gc & 1u;
           uint8_t* rowp = my_row0 + b * Cfg::STG_BYTES;
@@ -247,8 +262,12 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         } else {
           // fp16: two 32-column TMEM chunks fill one 32 x 64 staging box (128 B per row)
           const bool direct = (store == 2);          // experiment: 256-bit per-lane global stores, no smem staging
+          uint8_t* box_row0 = my_row0 + ((MV_GEMM_STG2 ? (bx & 1u) : 0u) * Cfg::STG_BYTES);
           if ((c & 1) == 0 && store == 1) {
-            if (lane == 0) bulk_wait_read_all();   // previous box has been read out of the staging buffer
+            if (lane == 0) {
+              if (MV_GEMM_STG2) bulk_wait_read_1();   // the box before the previous one has left this buffer
+              else bulk_wait_read_all();             // previous box has been read out of the staging buffer
+            }
             __syncwarp();
           }
           if (store && store != 4) {
@@ -293,17 +312,18 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
-                *reinterpret_cast<uint4*>(my_row0 + ((unit ^ sw) << 4)) =
+                *reinterpret_cast<uint4*>(box_row0 + ((unit ^ sw) << 4)) =
                     make_uint4(pkd[4 * u], pkd[4 * u + 1], pkd[4 * u + 2], pkd[4 * u + 3]);
               }
               if ((c & 1) && store != 3) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  tma_store_2d(&tmap_out, my_stg, col0 + (c >> 1) * 64, row0);
+                  tma_store_2d(&tmap_out, box_row0 - lane * 128, col0 + (c >> 1) * 64, row0);
                   bulk_commit_group();
                 }
               }
+              if (c & 1) ++bx;
             }
           } else if (store == 4 && (c & 1)) {          // experiment: stores without the math / staging writes
             __syncwarp();

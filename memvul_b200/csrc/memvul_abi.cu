@@ -355,6 +355,13 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   // stores, and the L2 prefetch does not shorten the residual wait (the TMA queue under load, not HBM, is the
   // latency); 0 = the r01 epilogue
   static const int ln_mode = [] { const char* e = getenv("MEMVUL_LN_MODE"); return e ? atoi(e) & 7 : 2; }();
+  // MEMVUL_LN_RING_SHORT: A/B ring depth (2..4) for K <= 1024 (see the kernel); longer K always uses all four stages
+  static const int ring_short = [] { const char* e = getenv("MEMVUL_LN_RING_SHORT"); int v = e ? atoi(e) : 4; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
+  const int ring = K <= 1024 ? ring_short : 4;
+  // MEMVUL_LN_RES: how the epilogue fetches the fp32 residual boxes: "tma" (default) or "ldgsts" (per-lane cp.async
+  // through the LSU path).  r02i: both wait ~3 k cycles per exposed box at K = 768 (and ~0.2 k with a 2-deep A/B ring that
+  // starves the MMA): the latency is the SM's own queue of outstanding operand bytes at the L2 port, whichever unit asks.
+  static const int res_ldgsts = [] { const char* e = getenv("MEMVUL_LN_RES"); return (e && strcmp(e, "ldgsts") == 0) ? 1 : 0; }();
   CUtensorMap ta, ta64, tb, tres, t32, t16;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 64, &ta64)) return rc;
@@ -371,7 +378,7 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 128 * 8, st));
   {
     LaunchScope ls(g_cls, st);
-    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16));
+    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4) | (ring << 12) | (res_ldgsts << 15), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16), resid);
     CUDA_TRY(cudaGetLastError());
   }
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
@@ -737,8 +744,8 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
                       const float* vterm, int B, int G, int H, int D, int same_idx, float* pooled, float* u,
                       float* uterm, uint64_t* best_key, float* logits, float* probs, int32_t* best_idx,
                       float* best_probs, int phase_mask, void* stream) {
-  if (B <= 0 || H <= 0 || D <= 0 || H % 128 != 0 || H > 768 || D % 4 != 0 || D > 512)
-    return fail(MEMVUL_E_INVALID, "pool_match needs H %% 128 == 0, H <= 768, D %% 4 == 0, D <= 512 (B=%d H=%d D=%d)", B, H, D);
+  if (B <= 0 || H <= 0 || D <= 0 || H % 128 != 0 || H > 768 || D % 4 != 0 || D > 1024)
+    return fail(MEMVUL_E_INVALID, "pool_match needs H %% 128 == 0, H <= 768, D %% 4 == 0, D <= 1024 (B=%d H=%d D=%d)", B, H, D);
   if (phase_mask <= 0 || phase_mask > MEMVUL_PM_ALL) return fail(MEMVUL_E_INVALID, "bad phase_mask %d", phase_mask);
   if ((phase_mask & (MEMVUL_PM_MATCH | MEMVUL_PM_FINAL)) &&
       (G <= 0 || !bank || !vterm || !logits || !probs || !best_key || !best_idx || !best_probs || !uterm))

@@ -214,6 +214,43 @@ __device__ __forceinline__ void match_phase(const PoolMatchParams& p, int gwarp,
 }
 
 
+// Generic match for feature widths the register-blocked phase does not cover (D > 512: ``use_header=False`` matches the
+// 768-wide pooled vectors directly, model_memory.py:69,101 -- unused by the shipped configs, so simple beats fast):
+// one warp per (query, anchor) pair, K over the lanes.
+__device__ __forceinline__ void match_phase_generic(const PoolMatchParams& p, int gwarp, int nwarps, int lane) {
+  const int D = p.D, G = p.G;
+  const float* wd0 = p.wproj + 2 * D;
+  const float* wd1 = p.wproj + 3 * D + 2 * D;
+  const long long items = static_cast<long long>(p.B) * G;
+  for (long long item = gwarp; item < items; item += nwarps) {
+    const int b = static_cast<int>(item / G), g = static_cast<int>(item - static_cast<long long>(b) * G);
+    const float* u = p.u + static_cast<size_t>(b) * D;
+    const float* v = p.bank + static_cast<size_t>(g) * D;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      const float d = fabsf(u[k] - __ldg(v + k));
+      a0 = fmaf(d, __ldg(wd0 + k), a0);
+      a1 = fmaf(d, __ldg(wd1 + k), a1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      const float l0 = a0 + p.uterm[b * 2 + 0] + __ldg(p.vterm + g * 2 + 0);
+      const float l1 = a1 + p.uterm[b * 2 + 1] + __ldg(p.vterm + g * 2 + 1);
+      const float m = fmaxf(l0, l1);
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      const float inv = 1.0f / (e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      const size_t o = (static_cast<size_t>(b) * G + g) * 2;
+      *reinterpret_cast<float2*>(p.logits + o) = make_float2(l0, l1);
+      *reinterpret_cast<float2*>(p.probs + o) = make_float2(p0, p1);
+      const float ps = p.same_idx == 0 ? p0 : p1;
+      atomicMax(p.best_key + b, (static_cast<unsigned long long>(__float_as_uint(ps)) << 32) |
+                                    static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(g)));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Tiled match for LARGE problems (BASELINE config 4: 256 queries x 16,384 anchors): the |u - v| term is O(B*G*512)
 // FP32 work, so what matters is operand reuse, like an SGEMM.  A block owns a 64-anchor tile of the bank in shared
@@ -394,6 +431,8 @@ __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p
     if (p.tiled) {
       extern __shared__ __align__(16) uint8_t dyn_smem[];
       match_phase_tiled(p, dyn_smem, sbest);
+    } else if (p.D > 512) {
+      match_phase_generic(p, gwarp, nwarps, lane);
     } else {
       match_phase(p, gwarp, nwarps, lane, sbest);
     }

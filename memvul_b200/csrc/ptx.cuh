@@ -275,6 +275,15 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, f
                "f"(a), "f"(b), "r"(cluster_mbar)
                : "memory");
 }
+// 16-byte asynchronous global -> shared copy through the LSU path (NOT the TMA unit, whose per-SM queue is shared with the
+// main loop's operand loads); completion is observed through cp_async_mbar_arrive on an mbarrier.
+__device__ __forceinline__ void cp_async_16B(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+// arrive on `bar` (without incrementing its pending count) once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Pull a TMA box into L2 without touching shared memory (a later cp.async.bulk.tensor of the same box hits L2).
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
@@ -330,6 +339,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's committed bulk groups have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent committed bulk group of this thread have finished reading shared memory (ping-pong staging)
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // erf(x) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): 2 MUFU + ~10 FP32 ops instead of erff()'s ~25.
 // Used only where the result is rounded to fp16 afterwards (GELU epilogue), where 1.5e-7 is invisible.
 __device__ __forceinline__ float rcp_approx(float x) {

@@ -276,14 +276,21 @@ class ModelMemory(Model):
         hidden, bad = self._encode(sample1)
         B, S, H = hidden.shape
         wp, bp, wh, bh = self._head_weights()
-        if not self._use_header:
-            raise NotImplementedError("use_header=False is not used by the MemVul configs")
         if flat_capacity is None:
             flat_capacity = self.shard_capacity
         bank = self._golden_instances_embeddings
-        out = native.pool_match(hidden, S * H, B, wp, bp, wh, bh, self._projector.weight, bank.contiguous(),
-                                self._bank_vterm(), same_idx=self._same_idx, phase_mask=native.PM_ALL,
-                                flat_capacity=flat_capacity)
+        if self._use_header:
+            out = native.pool_match(hidden, S * H, B, wp, bp, wh, bh, self._projector.weight, bank.contiguous(),
+                                    self._bank_vterm(), same_idx=self._same_idx, phase_mask=native.PM_ALL,
+                                    flat_capacity=flat_capacity)
+        else:
+            # use_header=False (model_memory.py:69,101): the 768-wide pooled vectors are matched directly; the POOL phase
+            # writes straight into the match's query buffer and the HEADER phase is skipped
+            pooled = torch.empty(B, H, dtype=torch.float32, device=hidden.device)
+            out = native.pool_match(hidden, S * H, B, wp, bp, None, None, self._projector.weight, bank.contiguous(),
+                                    self._bank_vterm(), same_idx=self._same_idx, u=pooled, pooled=pooled, D=H,
+                                    phase_mask=native.PM_POOL | native.PM_UTERM | native.PM_MATCH | native.PM_FINAL,
+                                    flat_capacity=flat_capacity)
         out["bad_mask"] = bad
         return out
 

@@ -274,13 +274,14 @@ def match_flat_layout(cap: int, G: int):
 
 def pool_match(cls: torch.Tensor, cls_stride: int, B: int, w_pool, b_pool, w_head, b_head, w_proj=None, bank=None,
                vterm=None, same_idx: int = 0, phase_mask: int = PM_ALL, u: Optional[torch.Tensor] = None,
-               pooled: Optional[torch.Tensor] = None, flat_capacity: Optional[int] = None):
+               pooled: Optional[torch.Tensor] = None, flat_capacity: Optional[int] = None, D: Optional[int] = None):
     """Fused pool + header + match.  Returns dict(u, pooled[, logits, probs, best_idx, best_probs]).
     ``flat_capacity``: allocate probs / best_probs / best_idx as views of ONE flat fp32 buffer (``out["_flat"]``) laid
     out by ``match_flat_layout(flat_capacity, G)`` -- what the multi-GPU gather sends as is."""
     dev = w_pool.device
     H = w_pool.shape[0]
-    D = w_head.shape[0] if w_head is not None else 4
+    if D is None:
+        D = w_head.shape[0] if w_head is not None else (u.shape[1] if u is not None else 4)
     G = 0 if bank is None else bank.shape[0]
     f = dict(dtype=torch.float32, device=dev)
     pooled = torch.empty(B, H, **f) if pooled is None else pooled

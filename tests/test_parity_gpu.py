@@ -393,3 +393,92 @@ def test_model_single_matches_the_reference_run(name):
         for k, v in j["metrics"].items():
             assert m[k] == pytest.approx(v, abs=1e-6), k
     print(f"{name}: logits err {err:.2e}, decision margin {margin:.2e}")
+
+
+def test_use_header_false_matches_the_oracle():
+    """model_memory.py:69,101: without the header the 768-wide pooled vectors are matched directly
+    (``_projector`` = Linear(3*768 -> 2)); unused by the shipped configs, but part of the constructor contract."""
+    from memvul_b200.custom_PTM_embedder import PretrainedTransformerEmbedder
+    from memvul_b200.model_memory import ModelMemory
+    from memvul_b200.modules import BasicTextFieldEmbedder
+    from memvul_b200.parity import gate_report
+    from memvul_b200.registrable import Vocabulary
+    from memvul_b200.synthetic import BERT_TINY, config_lite, synthetic_ids, synthetic_state_dict
+    from oracle import memvul_oracle as O
+    shape = BERT_TINY
+    sd = {k: v for k, v in synthetic_state_dict(shape).items() if not k.startswith("_projector")}
+    g = torch.Generator().manual_seed(11)
+    sd["_projector.weight"] = torch.randn(2, 3 * shape.hidden, generator=g) * 0.03
+    emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape))
+    model = ModelMemory(Vocabulary({"labels": ["same", "diff"]}), BasicTextFieldEmbedder({"tokens": emb}), use_header=False)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    assert model.get_output_dim() == shape.hidden and not hasattr(model, "_projector_single")
+    alens = [9, 33, 64, 17, 40, 5, 64]
+    a_ids, a_mask, _ = synthetic_ids(len(alens), 64, lens=alens, seed=31, vocab_size=shape.vocab_size)
+    lens = [64, 20, 3, 50, 64, 31]
+    ids, mask, tids = synthetic_ids(len(lens), 64, lens=lens, seed=32, vocab_size=shape.vocab_size)
+    with torch.no_grad():
+        model.forward_gold_instances(_dev(a_ids, a_mask), [{"type": "golden", "instance": [{"label": f"CWE-{i}"}]} for i in range(len(alens))])
+        out = model(sample1=_dev(ids, mask, tids), metadata=_meta(len(lens)))
+        bank = O.instance_forward(sd, a_ids, a_mask, None, shape, use_header=False)
+        u = O.instance_forward(sd, ids, mask, tids, shape, use_header=False)
+        ref = O.match(u, bank, sd["_projector.weight"], model._same_idx)
+    assert tuple(model._golden_instances_embeddings.shape) == (len(alens), shape.hidden)
+    dev = out["native"]["device"]
+    assert float((model._golden_instances_embeddings.cpu() - bank).abs().max()) < TOL
+    gr = gate_report(dev["logits"].cpu().numpy(), np.asarray(out["probs"].tolist()), out["native"]["best_idx"].tolist(),
+                     ref["logits"].numpy(), ref["p"].numpy(), model._same_idx, thresholds=(0.5,), tol=TOL)
+    assert gr["ok"] and gr["argmax_not_maximiser"] == 0, gr
+    rows = model.make_output_human_readable(out)
+    assert len(rows) == len(lens) and len(rows[0]["predict"]) == len(alens)
+
+
+def test_predict_single_driver_end_to_end(tmp_path_factory):
+    """BASELINE configs[0] plumbing (predict_single.py:46-97 + reader_single): archive -> reader -> batches of 4 ->
+    ModelSingle -> JSON lines -> cal_metrics, checked against the oracle's probabilities row by row."""
+    import tarfile
+    from memvul_b200 import predict_single as PS
+    from memvul_b200.synthetic import BERT_TINY_H512, synthetic_state_dict
+    from memvul_b200.tokenizer import build_tokenizer
+    from oracle import memvul_oracle as O
+    from toy_vocab import TOY_VOCAB
+    d = tmp_path_factory.mktemp("arch1")
+    vocab_file = d / "vocab.txt"
+    vocab_file.write_text("\n".join(TOY_VOCAB) + "\n")
+    (d / "vocabulary").mkdir()
+    (d / "vocabulary" / "class_labels.txt").write_text("neg\npos\n")
+    tok = {"type": "pretrained_transformer", "model_name": str(vocab_file), "add_special_tokens": True, "max_length": 128}
+    cfg = {"dataset_reader": {"type": "reader_single", "tokenizer": tok},
+           "model": {"type": "model_single", "device": "cuda:0", "text_field_embedder": {"token_embedders": {"tokens": {
+               "type": "custom_pretrained_transformer", "model_name": "bert-base-uncased", "pretrained_model_path": "",
+               "transformer_kwargs": {"vocab_size": 1024, "hidden_size": 128, "num_hidden_layers": 2,
+                                      "num_attention_heads": 2, "intermediate_size": 512}}}}},
+           "validation_data_loader": {"batch_size": 4, "shuffle": False}}
+    (d / "config.json").write_text(json.dumps(cfg))
+    sd = synthetic_state_dict(BERT_TINY_H512, model="single")
+    torch.save(sd, d / "weights.th")
+    with tarfile.open(d / "model.tar.gz", "w:gz") as t:
+        for n in ("config.json", "weights.th", "vocabulary"):
+            t.add(d / n, arcname=n)
+    words = ["buffer", "overflow", "parser", "sql", "injection", "crash", "null", "heap", "free", "fix"]
+    rows = [{"Issue_Url": f"u{i}", "Issue_Title": words[i % 10], "Issue_Body": " ".join(words[(i * 3) % 7:(i * 3) % 7 + 4]),
+             "Security_Issue_Full": int(i % 4 == 0)} for i in range(10)]
+    (d / "test_project.json").write_text(json.dumps(rows))
+    res = d / "single_result.json"
+    metrics = PS.test(str(d / "model.tar.gz"), str(d / "test_project.json"), predictions_output_file=str(res), batch_size=4, cuda_device=0)
+    lines = [json.loads(l) for l in res.read_text().splitlines()]
+    assert [len(l) for l in lines] == [4, 4, 2]                                   # batch=4 (configs[0])
+    flat = [r for l in lines for r in l]
+    assert [r["Issue_Url"] for r in flat] == ["u0", "u4", "u8", "u1", "u2", "u3", "u5", "u6", "u7", "u9"]   # label groups in first-seen order
+    assert all(set(r) == {"Issue_Url", "label", "predict", "prob"} for r in flat)
+    tk = build_tokenizer(tok)
+    by_url = {r["Issue_Url"]: r for r in rows}
+    for r in flat:
+        s = by_url[r["Issue_Url"]]
+        ids = torch.as_tensor(tk.ids(tk.tokenize(f"{s['Issue_Title']}. {s['Issue_Body']}")), dtype=torch.int64)[None]
+        ref = O.single_forward(sd, ids, torch.ones_like(ids, dtype=torch.bool), None, BERT_TINY_H512)
+        assert abs(r["prob"] - float(ref["probs"][0, 1])) < TOL and r["label"] == ("pos" if s["Security_Issue_Full"] else "neg")
+    assert "accuracy" in metrics and "pos_f1-score" in metrics
+    m = PS.cal_metrics(str(res))
+    assert m["TP"] + m["FN"] == 3 and m["TN"] + m["FP"] == 7
