@@ -790,6 +790,10 @@ int memvul_pool_match(const float* cls, int64_t cls_stride, const float* w_pool,
   if ((phase_mask & MEMVUL_PM_MATCH) && !(phase_mask & (MEMVUL_PM_POOL | MEMVUL_PM_UTERM)))
     CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(uint64_t) * B, st));
   const bool multi = (phase_mask & (phase_mask - 1)) != 0;
+  if (tiled) {        // Wd of both classes -> constant memory (pool_match.cuh: c_match_wd), stream-ordered
+    CUDA_TRY(cudaMemcpyToSymbolAsync(mv::c_match_wd, w_proj + 2 * D, sizeof(float) * D, 0, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(mv::c_match_wd, w_proj + 3 * D + 2 * D, sizeof(float) * D, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  }
   LaunchScope ls(KC_POOL_MATCH, st);
   if (multi) {
     void* args[] = {&p};

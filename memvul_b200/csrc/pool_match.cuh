@@ -41,52 +41,71 @@ struct PoolMatchParams {
   int B, G, H, D, same_idx, b_chunk, phase_mask, tiled;
 };
 
-// out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]).  Work item = (output column n, chunk of 8 rows b): the W row lives in
-// registers, the 8 dot products are independent chains (ILP) and their warp reductions interleave; with N * ceil(B/8)
-// items the phase spreads over every resident warp instead of serialising B rows per column.
+// out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]).  Work item = (chunk of 8 rows b, output column n), chunk-major; a block
+// takes a contiguous range of items, stages the chunk's 8 input rows in shared memory ONCE and lets its warps walk the
+// range's columns: the W row lives in registers, the 8 dot products are independent chains whose warp reductions
+// interleave.  (r01 read the 8 rows from global memory for every column: 151 MB of L2 traffic at B = 64 and 660 MB at
+// B = 256 for the pooler alone -- ~30 us and ~130 us of the launch.)
+constexpr int kDenseRows = 8, kDenseMaxK = 768;
 template <int ACT /*0 tanh, 1 relu*/>
 __device__ __forceinline__ void dense_rows_phase(const float* x, long long x_stride, const float* __restrict__ W,
                                                  const float* __restrict__ bias, float* out, int B, int N, int K,
-                                                 int gwarp, int nwarps, int lane) {
-  constexpr int MAXV = 6;                       // K <= 768
-  constexpr int BCH = 8;
-  const int nv = K >> 7;                        // float4 per lane (K multiple of 128)
+                                                 float* xs /* shared [kDenseRows * kDenseMaxK] */) {
+  constexpr int MAXV = kDenseMaxK / 128;        // K <= 768, multiple of 128
+  constexpr int BCH = kDenseRows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int nv = K >> 7;                        // float4 per lane
   const int nbc = (B + BCH - 1) / BCH;
-  const int items = N * nbc;
-  for (int item = gwarp; item < items; item += nwarps) {
-    const int n = item / nbc, b0 = (item - n * nbc) * BCH;
-    float4 w[MAXV];
+  const long long items = static_cast<long long>(N) * nbc;
+  const long long per = (items + gridDim.x - 1) / gridDim.x;
+  const long long i0 = blockIdx.x * per, i1 = min(items, i0 + per);
+  for (long long seg = i0; seg < i1;) {
+    const int chunk = static_cast<int>(seg / N);
+    const long long seg_end = min(i1, static_cast<long long>(chunk + 1) * N);
+    const int b0 = chunk * BCH;
+    __syncthreads();                            // the previous segment is done with xs
+    for (int i = threadIdx.x; i < BCH * (K >> 2); i += blockDim.x) {
+      const int r = i / (K >> 2), k4 = i - r * (K >> 2);
+      const int bb = min(b0 + r, B - 1);        // tail rows repeat the last row; never stored
+      reinterpret_cast<float4*>(xs)[r * (K >> 2) + k4] =
+          *reinterpret_cast<const float4*>(x + static_cast<size_t>(bb) * x_stride + k4 * 4);
+    }
+    __syncthreads();
+    for (long long item = seg + warp; item < seg_end; item += wpb) {
+      const int n = static_cast<int>(item - static_cast<long long>(chunk) * N);
+      float4 w[MAXV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-      w[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + i * 128 + lane * 4))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    float acc[BCH];
+      for (int i = 0; i < MAXV; ++i)
+        w[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + i * 128 + lane * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      float acc[BCH];
 #pragma unroll
-    for (int r = 0; r < BCH; ++r) acc[r] = 0.f;
+      for (int r = 0; r < BCH; ++r) acc[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      if (i < nv) {
+      for (int i = 0; i < MAXV; ++i) {
+        if (i < nv) {
 #pragma unroll
-        for (int r = 0; r < BCH; ++r) {
-          const int b = min(b0 + r, B - 1);     // tail rows recompute the last row; never stored
-          const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * x_stride + i * 128 + lane * 4);
-          acc[r] = fmaf(xv.x, w[i].x, acc[r]);
-          acc[r] = fmaf(xv.y, w[i].y, acc[r]);
-          acc[r] = fmaf(xv.z, w[i].z, acc[r]);
-          acc[r] = fmaf(xv.w, w[i].w, acc[r]);
+          for (int r = 0; r < BCH; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + r * K + i * 128 + lane * 4);
+            acc[r] = fmaf(xv.x, w[i].x, acc[r]);
+            acc[r] = fmaf(xv.y, w[i].y, acc[r]);
+            acc[r] = fmaf(xv.z, w[i].z, acc[r]);
+            acc[r] = fmaf(xv.w, w[i].w, acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < BCH; ++r) acc[r] = warp_sum(acc[r]);
+      const float bn = bias[n];
+#pragma unroll
+      for (int r = 0; r < BCH; ++r) {
+        if (lane == r && b0 + r < B) {
+          const float v = acc[r] + bn;
+          out[static_cast<size_t>(b0 + r) * N + n] = ACT == 0 ? tanhf(v) : fmaxf(v, 0.f);
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < BCH; ++r) acc[r] = warp_sum(acc[r]);
-    const float bn = bias[n];
-#pragma unroll
-    for (int r = 0; r < BCH; ++r) {
-      if (lane == r && b0 + r < B) {
-        const float v = acc[r] + bn;
-        out[static_cast<size_t>(b0 + r) * N + n] = ACT == 0 ? tanhf(v) : fmaxf(v, 0.f);
-      }
-    }
+    seg = seg_end;
   }
 }
 
@@ -257,13 +276,19 @@ __device__ __forceinline__ void match_phase_generic(const PoolMatchParams& p, in
 // memory (read from HBM exactly once per pass over the queries) and sweeps 64-query tiles against it, u arriving
 // in double-buffered 64-wide K chunks (cp.async); every thread keeps a 4 x 4 (query x anchor) register tile for
 // both classes.  Shared-memory rows are padded (+4 floats) so the 128-bit operand loads are conflict-free.
+// Wd (the |u - v| third of Linear(1536 -> 2), both classes) for the tiled match, in CONSTANT memory: every lane of a warp
+// multiplies by the same Wd[c][k], so the FFMAs take it as a constant-bank / uniform operand and the two LDS.128 per
+// 4-wide K step that fetched it from shared memory (2 of 10: the phase ran at the shared-memory wavefront limit, 0.50 of
+// the FP32 lane peak in r01) disappear.  Written by memvul_pool_match with a stream-ordered device-to-device copy before
+// every tiled launch; one model per device at a time may use the tiled path concurrently.
+__constant__ float c_match_wd[2 * 512];
+
 struct MatchTileCfg {
   static constexpr int BT = 64, GT = 64, KC = 64, D = 512;
   static constexpr int V_LD = D + 4, U_LD = KC + 4;
   static constexpr int OFF_V = 0;                                   // [GT][V_LD] floats
   static constexpr int OFF_U = OFF_V + GT * V_LD * 4;               // [2][BT][U_LD]
-  static constexpr int OFF_WD = OFF_U + 2 * BT * U_LD * 4;          // [2][D]
-  static constexpr int SMEM_BYTES = OFF_WD + 2 * D * 4;             // 171,008 B
+  static constexpr int SMEM_BYTES = OFF_U + 2 * BT * U_LD * 4;      // 166,912 B
 };
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
@@ -279,7 +304,6 @@ __device__ __forceinline__ void match_phase_tiled(const PoolMatchParams& p, uint
   using T = MatchTileCfg;
   float* sv = reinterpret_cast<float*>(smem + T::OFF_V);
   float* su = reinterpret_cast<float*>(smem + T::OFF_U);
-  float* swd = reinterpret_cast<float*>(smem + T::OFF_WD);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int B = p.B, G = p.G;
   const int n_bt = (B + T::BT - 1) / T::BT, n_gt = (G + T::GT - 1) / T::GT;
@@ -287,7 +311,6 @@ __device__ __forceinline__ void match_phase_tiled(const PoolMatchParams& p, uint
   // contiguous item ranges per block, anchor-tile major: consecutive items of a block share the bank tile
   const int per = (items + gridDim.x - 1) / gridDim.x;
   const int it0 = blockIdx.x * per, it1 = min(items, it0 + per);
-  for (int i = tid; i < 2 * T::D; i += blockDim.x) swd[i] = p.wproj[(i / T::D) * 3 * T::D + 2 * T::D + (i % T::D)];
   int cur_gt = -1;
   for (int item = it0; item < it1; ++item) {
     const int gt = item / n_bt, bt = item - gt * n_bt;
@@ -324,8 +347,8 @@ __device__ __forceinline__ void match_phase_tiled(const PoolMatchParams& p, uint
 #pragma unroll 4
       for (int k4 = 0; k4 < T::KC / 4; ++k4) {
         const int k = kc * T::KC + k4 * 4;
-        const float4 w0 = *reinterpret_cast<const float4*>(swd + k);
-        const float4 w1 = *reinterpret_cast<const float4*>(swd + T::D + k);
+        const float4 w0 = *reinterpret_cast<const float4*>(c_match_wd + k);            // constant bank: no LDS
+        const float4 w1 = *reinterpret_cast<const float4*>(c_match_wd + T::D + k);
         float4 uu[4], vv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) uu[i] = *reinterpret_cast<const float4*>(ub + (ty + 16 * i) * T::U_LD + k4 * 4);
@@ -397,15 +420,16 @@ __global__ void __launch_bounds__(256) pool_match_kernel(const PoolMatchParams p
     if (need_sync && multi) cg::this_grid().sync();
     need_sync = true;
   };
+  __shared__ __align__(16) float dense_xs[kDenseRows * kDenseMaxK];        // 24 KB: the 8 input rows of a dense-phase segment
   if (p.phase_mask & PM_POOL) {
     phase_sync();
-    dense_rows_phase<0>(p.cls, p.cls_stride, p.wp, p.bp, p.pooled, p.B, p.H, p.H, gwarp, nwarps, lane);
+    dense_rows_phase<0>(p.cls, p.cls_stride, p.wp, p.bp, p.pooled, p.B, p.H, p.H, dense_xs);
     if (p.best_key)
       for (int b = gtid; b < p.B; b += nthreads) p.best_key[b] = 0ull;
   }
   if (p.phase_mask & PM_HEADER) {
     phase_sync();
-    dense_rows_phase<1>(p.pooled, p.H, p.wh, p.bh, p.u, p.B, p.D, p.H, gwarp, nwarps, lane);
+    dense_rows_phase<1>(p.pooled, p.H, p.wh, p.bh, p.u, p.B, p.D, p.H, dense_xs);
   }
   if (p.phase_mask & PM_UTERM) {
     phase_sync();
