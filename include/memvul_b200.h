@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MEMVUL_ABI_VERSION 2
+#define MEMVUL_ABI_VERSION 3
 
 enum {
   MEMVUL_OK = 0,
@@ -37,14 +37,16 @@ enum {
 /* memvul_encoder_forward flags */
 enum {
   MEMVUL_ENC_CLS_ONLY = 1,  /* only the [CLS] row of every sequence is the last layer's output          */
-  MEMVUL_ENC_PACKED = 2     /* token-major var-len execution: padded tokens are never computed (needs row_start) */
+  MEMVUL_ENC_PACKED = 2,    /* token-major var-len execution: padded tokens are never computed (needs row_start) */
+  MEMVUL_ENC_PRECISE = 4    /* accuracy mode: split-fp16 operands (3 partial products per GEMM), fp32 between GEMMs */
 };
 
 /* GEMM epilogues (memvul_gemm_f16) */
 enum {
   MEMVUL_EPI_BIAS_F16 = 0,       /* out fp16 = A W^T + bias                    */
   MEMVUL_EPI_BIAS_GELU_F16 = 1,  /* out fp16 = gelu_erf(A W^T + bias)          */
-  MEMVUL_EPI_BIAS_RESID_F32 = 2  /* out fp32 = A W^T + bias + resid (fp32)     */
+  MEMVUL_EPI_BIAS_RESID_F32 = 2, /* out fp32 = A W^T + bias + resid (fp32)     */
+  MEMVUL_EPI_BIAS_F32 = 3        /* out fp32 = A W^T + bias                    */
 };
 
 /* pool/match phases (memvul_pool_match phase_mask); MEMVUL_PM_ALL runs as one cooperative launch */
@@ -96,6 +98,14 @@ size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S
  *   for the padding in every GEMM; here the embedding kernel writes the valid tokens of all sequences back to back
  *   (token-major, sequence b at rows row_start[b]..row_start[b+1]) and every kernel reads the row count from
  *   row_start[B] ON THE DEVICE, so no host synchronisation is needed and padded tokens cost nothing.
+ *   MEMVUL_ENC_PRECISE -- opt-in accuracy mode for checkpoints whose heads amplify the fp16-operand error beyond the
+ *   1e-3 logit tolerance (profiles/r02h_precision.json): every GEMM operand is split into two fp16 numbers
+ *   (a = a_hi + a_lo) and the three significant partial products are computed by the same tcgen05 kernels on
+ *   K-concatenated operands; the caller passes the layers' GEMM kernels as [N, 3K] fp16 = [W_hi | W_hi | W_lo]
+ *   (memvul_b200/native.py PackedBert(precise=True)).  Activations stay fp32 between the GEMMs and the attention runs
+ *   in fp32 on the CUDA cores: ~5.5x slower than the default path, max |d logit| ~7e-6 instead of ~2.7e-4 against the
+ *   fp32 reference (profiles/r02n_precision_split.json; the floor is the tensor core's own fp32 accumulation).
+ *   MEMVUL_ENC_CLS_ONLY is accepted (all rows are computed; hidden_out[b*S] is the guaranteed output).
  * Supported: H in {128, 768} (H % 128 == 0, head_dim == 64), S <= 512, S <= max_pos. */
 int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
                            const int32_t* lens, const int32_t* row_start, int B, int S, float* hidden_out,
@@ -139,6 +149,12 @@ int memvul_gemm_ln_f16(const void* a, const void* w, const float* bias, const fl
  * row_start NULL: padded layout (sequence b at rows b*S..); else packed layout (rows row_start[b]..+lens[b]). */
 int memvul_attention_f16(const void* qkv, const int32_t* lens, const int32_t* row_start, void* ctx, int B, int S,
                          int H, void* stream);
+/* Accuracy-mode building blocks (MEMVUL_ENC_PRECISE): the fp32 attention (qkv fp32 [rows,3H] -> ctx fp32 [rows,H], same
+ * layouts and masking as memvul_attention_f16) and the operand split out fp16 [M,3K] = [hi | lo | hi] of x fp32 [M,K]
+ * (gelu != 0: of gelu_erf(x)). */
+int memvul_attention_f32(const float* qkv, const int32_t* lens, const int32_t* row_start, float* ctx, int B, int S,
+                         int H, void* stream);
+int memvul_split3_f16(const float* x, void* out, int M, int K, int gelu, void* stream);
 /* x32/x16 = LayerNorm(y) rows; x32 or x16 may be NULL; in-place x32 == y allowed. */
 int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16,
                      int M, int H, void* stream);

@@ -161,12 +161,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const float4* bias4 = reinterpret_cast<const float4*>(bias + gcol);
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
           float* orow = reinterpret_cast<float*>(out) + static_cast<size_t>(row) * ldo + gcol;
-          const float* rrow = resid + static_cast<size_t>(row) * ldo + gcol;
+          const float* rrow = resid ? resid + static_cast<size_t>(row) * ldo + gcol : nullptr;   // nullptr: fp32 output without a residual (MEMVUL_EPI_BIAS_F32)
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = __ldg(bias4 + j);
-              const float4 x = *reinterpret_cast<const float4*>(rrow + 4 * j);
+              const float4 x = rrow ? *reinterpret_cast<const float4*>(rrow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
               float4 o;
               o.x = __uint_as_float(r[4 * j + 0]) + b.x + x.x;
               o.y = __uint_as_float(r[4 * j + 1]) + b.y + x.y;

@@ -207,8 +207,11 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                     strip_row0(t), kEvictFirst);
       }
     };
+    // store == 5: fp32 output WITHOUT a residual (MEMVUL_EPI_BIAS_F32, the accuracy mode's Q K V / FFN-up products):
+    // same staging / TMA-store path, nothing is loaded and the staging buffer is only written
+    const bool no_resid = (store == 5);
     if constexpr (Cfg::RESID) {
-      if (lane == 0 && store) {
+      if (lane == 0 && store && !no_resid) {
         issue_res_load(0);
         issue_res_load(1);
       }
@@ -236,11 +239,11 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
           const uint32_t b = gc & 1u;
           uint8_t* rowp = my_row0 + b * Cfg::STG_BYTES;
           if (store) {
-            mbar_wait_idle(&my_res_bar[b], (gc >> 1) & 1u, idle_epi);   // residual chunk has landed
+            if (!no_resid) mbar_wait_idle(&my_res_bar[b], (gc >> 1) & 1u, idle_epi);   // residual chunk has landed
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               float4* p = reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(u) ^ sw) << 4));
-              const float4 x = *p;
+              const float4 x = no_resid ? make_float4(0.f, 0.f, 0.f, 0.f) : *p;
               const float4 bb = *reinterpret_cast<const float4*>(bsm + 4 * u);
               float4 o;
               o.x = __uint_as_float(v[4 * u + 0]) + bb.x + x.x;
@@ -255,7 +258,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
               tma_store_2d(&tmap_out, my_stg + b * Cfg::STG_BYTES, col0 + c * 32, row0);
               bulk_commit_group();
               bulk_wait_read_all();                // this store has left the buffer: refill it with chunk gc+2
-              issue_res_load(gc + 2);
+              if (!no_resid) issue_res_load(gc + 2);
             }
           }
           ++gc;

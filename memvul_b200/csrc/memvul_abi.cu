@@ -19,6 +19,7 @@
 #include "gemm_tcgen05_2cta.cuh"
 #include "gemm_ln_tcgen05.cuh"
 #include "pool_match.cuh"
+#include "precise.cuh"
 #include "rowwise.cuh"
 
 namespace {
@@ -235,6 +236,7 @@ int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M
     case MEMVUL_EPI_BIAS_F16: return launch_gemm<BN, mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
     case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm<BN, mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
     case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm<BN, mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_F32: return launch_gemm<BN, mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, nullptr, out, sms, st, m_dev);
   }
   return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -262,9 +264,11 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   static const bool nostore = getenv("MEMVUL_GEMM_NOSTORE") != nullptr;      // experiment: time the main loop alone
   static const bool direct_st = getenv("MEMVUL_GEMM_DIRECT_ST") != nullptr;   // experiment: 256-bit per-lane stores
   CUtensorMap tout, tres;
+  const bool no_resid = Cfg::RESID && resid == nullptr;     // MEMVUL_EPI_BIAS_F32: fp32 output, nothing to add
   if (Cfg::RESID) {
     if (int rc = make_map(out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tout)) return rc;
-    if (int rc = make_map(resid, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tres)) return rc;
+    if (no_resid) tres = tout;
+    else if (int rc = make_map(resid, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32, 4, &tres)) return rc;
   } else {
     if (int rc = make_map(out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2, &tout)) return rc;
     tres = tout;
@@ -274,7 +278,7 @@ int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   if (tiles < clusters) clusters = tiles;
   LaunchScope ls(g_cls, st);
   kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, tres, M, N, K, bias,
-                                                              (nostore ? 0 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode())) | (gemm_wait_mode() << 8), out, m_dev);   // __cluster_dims__(2,1,1)
+                                                              (nostore ? 0 : (no_resid ? 5 : ((direct_st && !Cfg::RESID) ? 2 : epi_mode()))) | (gemm_wait_mode() << 8), out, m_dev);   // __cluster_dims__(2,1,1)
   CUDA_TRY(cudaGetLastError());
   return MEMVUL_OK;
 }
@@ -285,6 +289,7 @@ int launch_gemm_2cta_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, 
     case MEMVUL_EPI_BIAS_F16: return launch_gemm_2cta<mv::EPI_BIAS_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
     case MEMVUL_EPI_BIAS_GELU_F16: return launch_gemm_2cta<mv::EPI_BIAS_GELU_F16>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
     case MEMVUL_EPI_BIAS_RESID_F32: return launch_gemm_2cta<mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, resid, out, sms, st, m_dev);
+    case MEMVUL_EPI_BIAS_F32: return launch_gemm_2cta<mv::EPI_BIAS_RESID_F32>(ta, tb, M, N, K, bias, nullptr, out, sms, st, m_dev);
   }
   return fail(MEMVUL_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -567,6 +572,105 @@ Workspace carve(const memvul_bert_weights* w, int B, int S, void* base, int flag
   return ws;
 }
 
+// ------------------------------------------------------------------ accuracy mode (MEMVUL_ENC_PRECISE, precise.cuh)
+int split3_impl(const float* x, void* out, int M, int K, int act, cudaStream_t st, const int* m_dev) {
+  if (M <= 0 || K <= 0 || K % 4 != 0) return fail(MEMVUL_E_INVALID, "split3 needs M > 0 and K %% 4 == 0 (M=%d K=%d)", M, K);
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const long long total = static_cast<long long>(M) * (K / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > di.sms * 16LL) blocks = di.sms * 16LL;
+  LaunchScope ls(g_cls == KC_CLS_TAIL ? KC_CLS_TAIL : KC_LAYERNORM, st);
+  if (act == 1) mv::split3_rows_kernel<1><<<static_cast<int>(blocks), 256, 0, st>>>(x, reinterpret_cast<__half*>(out), M, K, m_dev);
+  else mv::split3_rows_kernel<0><<<static_cast<int>(blocks), 256, 0, st>>>(x, reinterpret_cast<__half*>(out), M, K, m_dev);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+int attention_f32_impl(const float* qkv, const int32_t* lens, const int32_t* row_start, float* ctx, int B, int S, int H,
+                       cudaStream_t st) {
+  if (B <= 0 || S <= 0 || S > 512) return fail(MEMVUL_E_INVALID, "attention needs 1 <= S <= 512 (B=%d S=%d)", B, S);
+  if (H % 64 != 0) return fail(MEMVUL_E_INVALID, "attention needs H %% 64 == 0 (head_dim 64), H=%d", H);
+  if (B > 65535) return fail(MEMVUL_E_INVALID, "fp32 attention takes at most 65535 sequences per call (B=%d)", B);
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_f32_kernel), mv::AttnF32Cfg::SMEM_BYTES)) return rc;
+  const int n_qt = (S + mv::AttnF32Cfg::BQ - 1) / mv::AttnF32Cfg::BQ;
+  LaunchScope ls(KC_ATTENTION, st);
+  mv::attention_f32_kernel<<<dim3(n_qt, H / 64, B), 256, mv::AttnF32Cfg::SMEM_BYTES, st>>>(qkv, lens, row_start, ctx, B, S, H, n_qt);
+  CUDA_TRY(cudaGetLastError());
+  return MEMVUL_OK;
+}
+
+struct PreciseWs {
+  float* x32;       // [M,H]   residual stream (token-major; the caller's hidden_out holds it in the padded layout)
+  __half* xs;       // [M,3H]  split operand of the QKV / attn-out / FFN-up GEMMs
+  float* qkv32;     // [M,3H]
+  float* ctx32;     // [M,H]
+  float* h32;       // [M,I]
+  __half* hs;       // [M,3I]  split GELU output = operand of the FFN-down GEMM
+  size_t bytes;
+};
+PreciseWs carve_precise(const memvul_bert_weights* w, int B, int S, void* base) {
+  const size_t M = static_cast<size_t>(B) * S, H = w->hidden, I = w->intermediate;
+  auto up = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  PreciseWs ws;
+  ws.x32 = reinterpret_cast<float*>(p + off); off += up(M * H * 4);
+  ws.xs = reinterpret_cast<__half*>(p + off); off += up(M * 3 * H * 2);
+  ws.qkv32 = reinterpret_cast<float*>(p + off); off += up(M * 3 * H * 4);
+  ws.ctx32 = reinterpret_cast<float*>(p + off); off += up(M * H * 4);
+  ws.h32 = reinterpret_cast<float*>(p + off); off += up(M * I * 4);
+  ws.hs = reinterpret_cast<__half*>(p + off); off += up(M * 3 * I * 2);
+  ws.bytes = off;
+  return ws;
+}
+
+// The encoder with split-fp16 operands (precise.cuh): same layer structure, every GEMM is a K' = 3K problem on the
+// tcgen05 kernels with fp32 output, everything between the GEMMs is fp32.  w->layer[*].w_* are the K-concatenated
+// [N, 3K] matrices [W_hi | W_hi | W_lo].
+int encoder_forward_precise(const memvul_bert_weights* w, const int64_t* token_ids, const int64_t* type_ids,
+                            const int32_t* lens, const int32_t* row_start, int B, int S, float* hidden_out,
+                            void* workspace, size_t workspace_bytes, int flags, int32_t* bad_flag, cudaStream_t st) {
+  const bool cls_only = (flags & MEMVUL_ENC_CLS_ONLY) != 0;
+  const bool packed = (flags & MEMVUL_ENC_PACKED) != 0;
+  PreciseWs ws = carve_precise(w, B, S, workspace);
+  if (ws.bytes > workspace_bytes)
+    return fail(MEMVUL_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  const int M = B * S, H = w->hidden, I = w->intermediate;
+  const int32_t* rs = packed ? row_start : nullptr;
+  const int* m_dev = packed ? row_start + B : nullptr;
+  float* x32 = packed ? ws.x32 : hidden_out;          // padded layout: the residual stream IS the output tensor
+  // K1 (the fp16 copy it also writes is not used in this mode: it lands in the hs scratch)
+  if (int rc = embed_impl(w, token_ids, type_ids, lens, rs, B, S, x32, ws.hs, bad_flag, st)) return rc;
+  for (int l = 0; l < w->layers; ++l) {
+    const memvul_bert_layer& L = w->layer[l];
+    if (int rc = split3_impl(x32, ws.xs, M, H, 0, st, m_dev)) return rc;
+    { ClassScope cs(KC_GEMM_QKV);
+      if (int rc = gemm_impl(ws.xs, L.w_qkv, L.b_qkv, nullptr, ws.qkv32, M, 3 * H, 3 * H, MEMVUL_EPI_BIAS_F32, st, m_dev)) return rc; }
+    if (int rc = attention_f32_impl(ws.qkv32, lens, rs, ws.ctx32, B, S, H, st)) return rc;
+    if (int rc = split3_impl(ws.ctx32, ws.xs, M, H, 0, st, m_dev)) return rc;
+    { ClassScope cs(KC_GEMM_ATTN_OUT);
+      if (int rc = gemm_impl(ws.xs, L.w_ao, L.b_ao, x32, x32, M, H, 3 * H, MEMVUL_EPI_BIAS_RESID_F32, st, m_dev)) return rc; }
+    if (int rc = layernorm_impl(x32, L.ln1_g, L.ln1_b, w->ln_eps, x32, nullptr, M, H, st)) return rc;
+    if (int rc = split3_impl(x32, ws.xs, M, H, 0, st, m_dev)) return rc;
+    { ClassScope cs(KC_GEMM_FFN_UP);
+      if (int rc = gemm_impl(ws.xs, L.w_ff1, L.b_ff1, nullptr, ws.h32, M, I, 3 * H, MEMVUL_EPI_BIAS_F32, st, m_dev)) return rc; }
+    if (int rc = split3_impl(ws.h32, ws.hs, M, I, 1, st, m_dev)) return rc;
+    { ClassScope cs(KC_GEMM_FFN_DOWN);
+      if (int rc = gemm_impl(ws.hs, L.w_ff2, L.b_ff2, x32, x32, M, H, 3 * I, MEMVUL_EPI_BIAS_RESID_F32, st, m_dev)) return rc; }
+    if (int rc = layernorm_impl(x32, L.ln2_g, L.ln2_b, w->ln_eps, x32, nullptr, M, H, st)) return rc;
+  }
+  if (packed) {
+    LaunchScope ls(KC_OTHER, st);
+    if (cls_only) mv::scatter_cls_rows_kernel<<<B, 192, 0, st>>>(ws.x32, row_start, hidden_out, B, S, H);
+    else mv::unpack_rows_kernel<<<(M + 7) / 8, 256, 0, st>>>(ws.x32, row_start, lens, hidden_out, B, S, H);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return MEMVUL_OK;
+}
+
 int check_weights(const memvul_bert_weights* w) {
   if (!w || !w->layer) return fail(MEMVUL_E_INVALID, "null weights");
   if (w->hidden != 768 && w->hidden != 128) return fail(MEMVUL_E_INVALID, "hidden must be 768 or 128, got %d", w->hidden);
@@ -585,6 +689,7 @@ const char* memvul_last_error(void) { return g_err; }
 
 size_t memvul_encoder_workspace_bytes(const memvul_bert_weights* w, int B, int S, int flags) {
   if (!w || B <= 0 || S <= 0) return 0;
+  if (flags & MEMVUL_ENC_PRECISE) return carve_precise(w, B, S, nullptr).bytes;
   return carve(w, B, S, nullptr, flags).bytes;
 }
 
@@ -606,6 +711,17 @@ int memvul_attention_f16(const void* qkv, const int32_t* lens, const int32_t* ro
                          int H, void* stream) {
   if (!qkv || !lens || !ctx) return fail(MEMVUL_E_INVALID, "attention null pointer");
   return attention_impl(qkv, lens, row_start, ctx, B, S, H, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_attention_f32(const float* qkv, const int32_t* lens, const int32_t* row_start, float* ctx, int B, int S,
+                         int H, void* stream) {
+  if (!qkv || !lens || !ctx) return fail(MEMVUL_E_INVALID, "attention null pointer");
+  return attention_f32_impl(qkv, lens, row_start, ctx, B, S, H, static_cast<cudaStream_t>(stream));
+}
+
+int memvul_split3_f16(const float* x, void* out, int M, int K, int gelu, void* stream) {
+  if (!x || !out) return fail(MEMVUL_E_INVALID, "split3 null pointer");
+  return split3_impl(x, out, M, K, gelu ? 1 : 0, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 int memvul_layernorm(const float* y, const float* gamma, const float* beta, float eps, float* x32, void* x16, int M,
@@ -650,6 +766,9 @@ int memvul_encoder_forward(const memvul_bert_weights* w, const int64_t* token_id
   const bool cls_only = (flags & MEMVUL_ENC_CLS_ONLY) != 0;
   const bool packed = (flags & MEMVUL_ENC_PACKED) != 0;
   if (packed && !row_start) return fail(MEMVUL_E_INVALID, "MEMVUL_ENC_PACKED needs row_start (memvul_mask_to_lens fills it)");
+  if (flags & MEMVUL_ENC_PRECISE)
+    return encoder_forward_precise(w, token_ids, type_ids, lens, row_start, B, S, hidden_out, workspace, workspace_bytes,
+                                   flags, bad_flag, static_cast<cudaStream_t>(stream));
   Workspace ws = carve(w, B, S, workspace, flags);
   if (ws.bytes > workspace_bytes)
     return fail(MEMVUL_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);

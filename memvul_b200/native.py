@@ -19,10 +19,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmemvul_b200.so")
 SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh",
-           "attention_tcgen05_v2.cuh", "rowwise.cuh", "pool_match.cuh"]
+           "attention_tcgen05_v2.cuh", "rowwise.cuh", "pool_match.cuh", "precise.cuh"]
 
-ABI_VERSION = 2
-EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32 = 0, 1, 2
+ABI_VERSION = 3
+EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
 PM_POOL, PM_HEADER, PM_UTERM, PM_MATCH, PM_FINAL, PM_ALL = 1, 2, 4, 8, 16, 31
 
 _lock = threading.Lock()
@@ -70,7 +70,8 @@ class BertWeightsC(ctypes.Structure):
 
 EXPORTS = ["memvul_abi_version", "memvul_last_error", "memvul_encoder_workspace_bytes", "memvul_encoder_forward",
            "memvul_mask_to_lens", "memvul_bank_prepare", "memvul_pool_match", "memvul_single_head",
-           "memvul_gemm_f16", "memvul_gemm_ln_f16", "memvul_attention_f16", "memvul_layernorm", "memvul_embed_layernorm",
+           "memvul_gemm_f16", "memvul_gemm_ln_f16", "memvul_attention_f16", "memvul_attention_f32", "memvul_split3_f16",
+           "memvul_layernorm", "memvul_embed_layernorm",
            "memvul_launch_count", "memvul_profile_enable", "memvul_profile_read"]
 KERNEL_CLASSES = ["embed_ln", "gemm_qkv", "attention", "gemm_attn_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down",
                   "pool_match", "other", "attention_cls", "cls_tail"]
@@ -99,6 +100,8 @@ def lib() -> ctypes.CDLL:
             L.memvul_gemm_f16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
             L.memvul_gemm_ln_f16.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]
             L.memvul_attention_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+            L.memvul_attention_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+            L.memvul_split3_f16.argtypes = [vp, vp, i32, i32, i32, vp]
             L.memvul_layernorm.argtypes = [vp, vp, vp, f32, vp, vp, i32, i32, vp]
             L.memvul_embed_layernorm.argtypes = [ctypes.POINTER(BertWeightsC), vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
             L.memvul_launch_count.restype = ctypes.c_longlong
@@ -144,19 +147,33 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------- weights
+def split3_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] -> fp16 [N,3K] = [hi | hi | lo] with hi = fp16(w), lo = fp16(w - hi): the weight side of the
+    split-fp16 accuracy mode (the activation side is [hi | lo | hi], so the K' = 3K product is
+    a_hi w_hi + a_lo w_hi + a_hi w_lo)."""
+    w = w.to(torch.float32)
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
 class PackedBert:
     """Device-resident BERT weights in the layout the kernels read: fp16 [out,in] GEMM kernels with
     query|key|value fused into one [3H,H] matrix, fp32 biases / LayerNorm / embedding tables.
     Built from a ``state_dict`` with HF ``BertModel`` names under ``prefix``."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, device: torch.device, ln_eps: float = 1e-12):
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, device: torch.device, ln_eps: float = 1e-12,
+                 precise: bool = False):
         def f32(k):
             return sd[prefix + k].detach().to(device=device, dtype=torch.float32).contiguous()
 
         def f16(t):
-            return t.to(torch.float16).contiguous()
+            # accuracy mode (MEMVUL_ENC_PRECISE): [N, 3K] = [W_hi | W_hi | W_lo], the K-concatenated split operand that
+            # pairs with the activations' [A_hi | A_lo | A_hi] (memvul_b200/csrc/precise.cuh)
+            return split3_weight(t) if precise else t.to(torch.float16).contiguous()
 
         self.device = device
+        self.precise = bool(precise)
         self.word = f32("embeddings.word_embeddings.weight")
         self.pos = f32("embeddings.position_embeddings.weight")
         self.type = f32("embeddings.token_type_embeddings.weight")
@@ -224,7 +241,11 @@ def raise_for_flag(flag: int) -> None:
                          "(torch.embedding raises in the reference; custom_PTM_embedder.py:205 for type ids)")
 
 
-ENC_CLS_ONLY, ENC_PACKED = 1, 2
+ENC_CLS_ONLY, ENC_PACKED, ENC_PRECISE = 1, 2, 4
+
+
+def encoder_flags(w: PackedBert, cls_only: bool, packed: bool) -> int:
+    return (ENC_CLS_ONLY if cls_only else 0) | (ENC_PACKED if packed else 0) | (ENC_PRECISE if w.precise else 0)
 
 
 def encoder_forward(w: PackedBert, token_ids: torch.Tensor, lens: torch.Tensor,
@@ -240,7 +261,7 @@ def encoder_forward(w: PackedBert, token_ids: torch.Tensor, lens: torch.Tensor,
     if type_ids is not None:
         _need(type_ids, torch.int64, "type_ids")
     B, S = token_ids.shape
-    flags = (ENC_CLS_ONLY if cls_only else 0) | (ENC_PACKED if row_start is not None else 0)
+    flags = encoder_flags(w, cls_only, row_start is not None)   # a PackedBert(precise=True) selects the accuracy mode
     need = w.workspace_bytes(B, S, flags)
     if workspace is None or workspace.numel() < need:
         workspace = torch.zeros(need, dtype=torch.uint8, device=token_ids.device)   # zero-init: header contract (PACKED)
@@ -336,7 +357,7 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int
     M, K = a.shape
     N = w.shape[0]
     if out is None:
-        out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_BIAS_RESID_F32 else torch.float16,
+        out = torch.empty(M, N, dtype=torch.float32 if epilogue in (EPI_BIAS_RESID_F32, EPI_BIAS_F32) else torch.float16,
                           device=a.device)
     with _on(a):
         _check(lib().memvul_gemm_f16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid), out.data_ptr(), M, N, K,
@@ -370,6 +391,28 @@ def attention_f16(qkv: torch.Tensor, lens: torch.Tensor, B: int, S: int, H: int,
         _check(lib().memvul_attention_f16(qkv.data_ptr(), lens.data_ptr(), _ptr(row_start), ctx.data_ptr(), B, S, H,
                                           _stream(qkv)))
     return ctx
+
+
+def attention_f32(qkv: torch.Tensor, lens: torch.Tensor, B: int, S: int, H: int,
+                  row_start: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accuracy-mode attention: qkv fp32 [rows,3H] -> ctx fp32 [rows,H] (same layouts as ``attention_f16``)."""
+    _need(qkv, torch.float32, "qkv")
+    _need(lens, torch.int32, "lens")
+    ctx = torch.zeros(qkv.shape[0], H, dtype=torch.float32, device=qkv.device)
+    with _on(qkv):
+        _check(lib().memvul_attention_f32(qkv.data_ptr(), lens.data_ptr(), _ptr(row_start), ctx.data_ptr(), B, S, H,
+                                          _stream(qkv)))
+    return ctx
+
+
+def split3_f16(x: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    """fp32 [M,K] -> fp16 [M,3K] = [hi | lo | hi] (of gelu_erf(x) when ``gelu``): the activation side of the accuracy mode."""
+    _need(x, torch.float32, "x")
+    M, K = x.shape
+    out = torch.empty(M, 3 * K, dtype=torch.float16, device=x.device)
+    with _on(x):
+        _check(lib().memvul_split3_f16(x.data_ptr(), out.data_ptr(), M, K, 1 if gelu else 0, _stream(x)))
+    return out
 
 
 def layernorm(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-12):

@@ -135,15 +135,18 @@ def config_lite(shape: "BertShape"):
                           layer_norm_eps=shape.ln_eps)
 
 
-def build_memory_model(shape: "BertShape" = None, seed: int = 2021, same_first: bool = True, device=None):
-    """A ``ModelMemory`` with seeded weights: the object bench.py / smoke() / the parity tests drive."""
+def build_memory_model(shape: "BertShape" = None, seed: int = 2021, same_first: bool = True, device=None,
+                       precision: Optional[str] = None):
+    """A ``ModelMemory`` with seeded weights: the object bench.py / smoke() / the parity tests drive.
+    ``precision``: the embedder's arithmetic ("fp16" default, "split_fp16" = the opt-in accuracy mode)."""
     from .custom_PTM_embedder import PretrainedTransformerEmbedder
     from .model_memory import ModelMemory
     from .modules import BasicTextFieldEmbedder
     from .registrable import Vocabulary
     shape = shape or BERT_BASE
     vocab = Vocabulary({"labels": ["same", "diff"] if same_first else ["diff", "same"]})
-    emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape))
+    emb = PretrainedTransformerEmbedder("bert-base-uncased", pretrained_model_path="", config=config_lite(shape),
+                                        precision=precision)
     model = ModelMemory(vocab, BasicTextFieldEmbedder({"tokens": emb}), device=str(device or "cpu"), header_dim=shape.header)
     sd = synthetic_state_dict(shape, seed)
     load_into(model, sd)

@@ -32,7 +32,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
 
 def test_argument_validation_without_gpu(native_lib):
     L = native_lib
-    assert L.memvul_abi_version() == 2
+    assert L.memvul_abi_version() == 3
     assert L.memvul_gemm_f16(None, None, None, None, None, 128, 100, 64, 0, None) == -1
     assert b"N % 128" in L.memvul_last_error()
     assert L.memvul_gemm_f16(None, None, None, None, None, 128, 128, 60, 0, None) == -1
@@ -43,6 +43,8 @@ def test_argument_validation_without_gpu(native_lib):
     assert L.memvul_pool_match(None, 0, None, None, None, None, None, None, None, 4, 3, 768, 512, 2,
                                None, None, None, None, None, None, None, None, 1, None) == -1
     assert L.memvul_bank_prepare(None, None, 0, 512, None, None) == -1
+    assert L.memvul_attention_f32(None, None, None, None, 1, 128, 768, None) == -1
+    assert L.memvul_split3_f16(None, None, 4, 128, 0, None) == -1
     assert L.memvul_launch_count() == 0
 
 
@@ -58,6 +60,31 @@ def test_workspace_size_formula(native_lib):
     assert w.workspace_bytes(4, 128) == base and w.workspace_bytes(4, 128, native.ENC_PACKED | native.ENC_CLS_ONLY) == base
     assert w.workspace_bytes(4, 128, native.ENC_PACKED) == base + up(M * H * 4)     # packed residual stream to unpack
     assert w.hidden == 128 and w.layers == 2 and w.heads == 2 and w.intermediate == 512
+    # accuracy mode: fp32 residual + split operand [M,3H] + fp32 qkv / ctx / FFN intermediate + split GELU output [M,3I]
+    precise = up(M * H * 4) + up(M * 3 * H * 2) + up(M * 3 * H * 4) + up(M * H * 4) + up(M * I * 4) + up(M * 3 * I * 2)
+    assert w.workspace_bytes(4, 128, native.ENC_PRECISE | native.ENC_PACKED | native.ENC_CLS_ONLY) == precise
+
+
+def test_split_weight_layout():
+    """[W_hi | W_hi | W_lo] against [A_hi | A_lo | A_hi]: the K-concatenated product equals the three significant partial
+    products, and hi + lo restores the fp32 value to ~2^-22."""
+    import torch
+    from memvul_b200 import native
+    torch.manual_seed(0)
+    w = torch.randn(16, 64) * 0.05
+    a = torch.randn(8, 64)
+    w3 = native.split3_weight(w)
+    assert w3.shape == (16, 192) and w3.dtype == torch.float16
+    hi, hi2, lo = w3[:, :64].float(), w3[:, 64:128].float(), w3[:, 128:].float()
+    assert torch.equal(hi, hi2)
+    assert float(((hi + lo) - w).abs().max()) <= float(w.abs().max()) * 2.0 ** -21
+    a_hi = a.half().float()
+    a_lo = (a - a_hi).half().float()
+    a3 = torch.cat([a_hi, a_lo, a_hi], 1)
+    ref = a.double() @ w.double().T
+    got = a3.double() @ w3.double().T
+    plain = a_hi.double() @ hi.double().T
+    assert float((got - ref).abs().max()) < 2e-6 < float((plain - ref).abs().max())
 
 
 def test_no_cpu_fallback():

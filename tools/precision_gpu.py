@@ -34,12 +34,18 @@ def match64(u, bank, w, same):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "split_fp16"],
+                    help="split_fp16 = the opt-in accuracy mode (MEMVUL_ENC_PRECISE)")
+    ap.add_argument("--rows", type=int, default=0, help="use only the first N rows of the fixture (the accuracy mode is slow)")
     args = ap.parse_args()
     z = np.load(os.path.join(ROOT, "tests", "golden", "precision_u1024.npz"))
     u_ref, bank_ref = torch.from_numpy(z["u"]), torch.from_numpy(z["bank"])
     seed, n_rows = int(z["seed"]), int(z["rows"])
+    if args.rows:
+        n_rows = min(n_rows, args.rows // 64 * 64)
+        u_ref = u_ref[:n_rows]
     dev = torch.device("cuda:0")
-    model, sd = build_memory_model(BERT_BASE, device=dev)
+    model, sd = build_memory_model(BERT_BASE, device=dev, precision=args.precision)
     a_ids, a_mask, alens, *_ = c2_inputs()
     us = []
     with torch.no_grad():
@@ -58,7 +64,9 @@ def main():
     bank_dev = model._golden_instances_embeddings
     same = model._same_idx
     rep = {"rows": n_rows, "anchors": int(bank_ref.shape[0]), "seq_len": 512,
-           "arithmetic": "fp16 operands (kind::f16), fp32 TMEM accumulation, fp32 residual stream / LayerNorm / softmax statistics; pooler, header and match in fp32",
+           "arithmetic": ("fp16 operands (kind::f16), fp32 TMEM accumulation, fp32 residual stream / LayerNorm / softmax statistics; pooler, header and match in fp32"
+                          if args.precision == "fp16" else
+                          "accuracy mode: split-fp16 operands (3 partial products per GEMM on the kind::f16 kernels), fp32 attention / GELU / LayerNorm; pooler, header and match in fp32"),
            "u_err": {"max": float((u_dev.cpu() - u_ref).abs().max()), "p999": float(torch.quantile((u_dev.cpu() - u_ref).abs().flatten()[::7], 0.999)),
                      "mean": float((u_dev.cpu() - u_ref).abs().mean())},
            "bank_err": {"max": float((bank_dev.cpu() - bank_ref).abs().max())}, "scales": {}}
