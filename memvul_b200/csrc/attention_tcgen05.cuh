@@ -59,6 +59,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     if (tracing && g < 128u) trace[slot * 1024 + g * 8 + k] = static_cast<unsigned long long>(clock64());
   };
   const int idle_tma = wait_mode & 3, idle_mma = (wait_mode >> 2) & 3, idle_sm = (wait_mode >> 4) & 3;   // see mbar_wait_idle
+  const int stagger = wait_mode >> 10;                     // cycles the SM's second CTA delays its soft-max stream (0 = off)
+  const bool early = ((wait_mode >> 8) & 1) != 0;          // soft-max warps test pv_done / s_full early (non-blocking)
+  const bool spec = ((wait_mode >> 9) & 1) != 0;           // exponentials start against the stale row maximum (see below)
 
   extern __shared__ __align__(1024) uint8_t smem[];        // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -219,6 +222,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     bool store_pending = false;                                // this warp has a ctx TMA store reading its P rows
     // lens[] of the NEXT item is loaded one item ahead: the dependent global load (~650 cycles in the r01p trace) sat
     // on the serial path between two items
+    if (stagger > 0) {
+      // Which of the SM's two CTAs am I?  The hardware warp slot: the first CTA's six warps occupy slots 0-5.  (A wrong
+      // guess only loses the interleaving, never correctness.)
+      uint32_t wslot;
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+      if (wslot >= static_cast<uint32_t>(C::THREADS / 32)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger) {}
+      }
+    }
     int len_next = 0, rb_next = 0;
     if (static_cast<int>(blockIdx.x) < n_items) {
       const int b0 = blockIdx.x / (n_qt * n_heads);
@@ -257,9 +270,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         __syncwarp();
         store_pending = false;
       }
+      uint32_t s_ok = 0;                                       // early (non-blocking) test of this block's s_full, see below
       for (int j = 0; j < nkb; ++j, ++g) {
         if (warp_idx == 0 && lane == 0) stamp(g, 0, 0);
-        mbar_wait_idle(&s_full[g & 1u], (g >> 1) & 1u, idle_sm);
+        if (!__all_sync(0xffffffffu, s_ok != 0u)) mbar_wait_idle(&s_full[g & 1u], (g >> 1) & 1u, idle_sm);
         tc_fence_after();
         if (warp_idx == 0 && lane == 0) stamp(g, 0, 1);
         uint32_t s[2][32];
@@ -276,54 +290,80 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             for (int i = 0; i < 32; ++i)
               if (cc * 32 + i >= valid) s[cc][i] = 0xff800000u;   // -inf: exp2 -> 0, never the max
         }
+        // Early phase tests: P V of block g-1 was issued a whole block ago and Q K^T of block g+1 right after it, so both
+        // barriers have almost always completed when they are needed -- but a blocking try_wait still costs its ~90-180
+        // cycle round trip on this warp's serial chain.  test_wait is scoreboarded: issued before the last exponentials
+        // its latency hides under them, and the blocking wait is only the fallback.
+        uint32_t pv_ok = 0;
+        uint8_t* p_row = smem + C::OFF_P + (g & 1u) * C::P_BYTES + r * 128;   // P[g&1]: P V of block g-2 retired long ago
+        // P = 2^(s c - mc) -> swizzled fp16 row of the P buffer; returns the row's partial sum
+        auto exp_pass = [&](float mc) -> float {
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial sums (ILP)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                      // 8 columns -> one 16 B unit of the swizzled row
+              if (cc == 1 && u == 3 && early && j > 0) pv_ok = mbar_test_wait(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+              float e[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                e[t] = ex2_approx(fmaf(__uint_as_float(s[cc][u * 8 + t]), c, -mc));   // ex2(-inf) = 0 for masked keys
+              l4[0] += e[0] + e[1];
+              l4[1] += e[2] + e[3];
+              l4[2] += e[4] + e[5];
+              l4[3] += e[6] + e[7];
+              uint4 pk;
+              pk.x = pack_half2(e[0], e[1]);
+              pk.y = pack_half2(e[2], e[3]);
+              pk.z = pack_half2(e[4], e[5]);
+              pk.w = pack_half2(e[6], e[7]);
+              const int unit = cc * 4 + u;                     // 16 B unit inside the 64-column row
+              *reinterpret_cast<uint4*>(p_row + ((unit ^ (r & 7)) << 4)) = pk;
+            }
+          }
+          return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        };
         // row max: 4 independent chains of 3-input max (one chain of dependent FMNMX would be latency-bound)
-        float mx4[4];
+        auto row_max = [&]() -> float {
+          float mx4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t* sp = &s[q >> 1][(q & 1) * 16];
-          float m = __uint_as_float(sp[0]);
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t* sp = &s[q >> 1][(q & 1) * 16];
+            float m = __uint_as_float(sp[0]);
 #pragma unroll
-          for (int i = 1; i < 15; i += 2) m = max3(m, __uint_as_float(sp[i]), __uint_as_float(sp[i + 1]));
-          mx4[q] = fmaxf(m, __uint_as_float(sp[15]));
-        }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            for (int i = 1; i < 15; i += 2) m = max3(m, __uint_as_float(sp[i]), __uint_as_float(sp[i + 1]));
+            mx4[q] = fmaxf(m, __uint_as_float(sp[15]));
+          }
+          return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        };
         // Lazy rescaling: keep exponentiating against the stale reference m_run until some row's maximum has grown by
         // more than 2^8 relative to it (P <= 256 stays far inside fp16, O / l accumulate in fp32 and the common factor
         // cancels in O / l).  With a fresh maximum in almost every block, rescaling O in TMEM every time cost as many
         // FMULs as the exponentials themselves plus a TMEM load/store round trip on the critical path.
-        const bool grow = (mx - m_run) * c > 8.0f;             // true on the first block (m_run = -inf)
+        // Speculation (blocks after an item's first): since the stale reference is almost always kept, the exponentials
+        // start against it IMMEDIATELY and the row maximum (170 cycles of dependent FMNMX on this warp's serial chain) is
+        // computed in their shadow; only a row whose maximum did jump by > 2^8 repeats its 64 exponentials.
+        float mx, l_blk;
+        bool grow;
+        if (spec && j > 0) {
+          l_blk = exp_pass(m_run * c);
+          mx = row_max();
+          grow = (mx - m_run) * c > 8.0f;
+          if (grow) l_blk = exp_pass(mx * c);
+        } else {
+          mx = row_max();
+          grow = (mx - m_run) * c > 8.0f;                      // true on the first block (m_run = -inf)
+          l_blk = exp_pass((grow ? mx : m_run) * c);
+        }
         const bool any_grow = __any_sync(0xffffffffu, grow);
         const float m_new = grow ? mx : m_run;
         if (warp_idx == 0 && lane == 0) stamp(g, 0, 3);
-        const float mc = m_new * c;
-        uint8_t* p_row = smem + C::OFF_P + (g & 1u) * C::P_BYTES + r * 128;   // P[g&1]: P V of block g-2 retired long ago
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};                   // independent partial sums (ILP)
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {                        // 8 columns -> one 16 B unit of the swizzled row
-            float e[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-              e[t] = ex2_approx(fmaf(__uint_as_float(s[cc][u * 8 + t]), c, -mc));   // ex2(-inf) = 0 for masked keys
-            l4[0] += e[0] + e[1];
-            l4[1] += e[2] + e[3];
-            l4[2] += e[4] + e[5];
-            l4[3] += e[6] + e[7];
-            uint4 pk;
-            pk.x = pack_half2(e[0], e[1]);
-            pk.y = pack_half2(e[2], e[3]);
-            pk.z = pack_half2(e[4], e[5]);
-            pk.w = pack_half2(e[6], e[7]);
-            const int unit = cc * 4 + u;                       // 16 B unit inside the 64-column row
-            *reinterpret_cast<uint4*>(p_row + ((unit ^ (r & 7)) << 4)) = pk;
-          }
-        }
-        const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         if (warp_idx == 0 && lane == 0) stamp(g, 0, 4);
         const float alpha = ex2_approx((m_run - m_new) * c);   // 0 on the first block (m_run = -inf), else 1 unless grown
+        s_ok = (early && j + 1 < nkb) ? mbar_test_wait(&s_full[(g + 1) & 1u], ((g + 1) >> 1) & 1u) : 0u;   // consumed at the next loop top
         if (j > 0) {
-          mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);   // O holds blocks 0..j-1 of this item
+          if (!__all_sync(0xffffffffu, pv_ok != 0u))
+            mbar_wait_idle(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u, idle_sm);   // O holds blocks 0..j-1 of this item
           tc_fence_after();
           if (any_grow) {
 #pragma unroll

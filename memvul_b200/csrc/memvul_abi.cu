@@ -399,7 +399,17 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
 // softmax warps; 0 spin, 1 suspend hint, 2 hint + nanosleep -- ptx.cuh mbar_wait_idle)
 static int att_wait_mode() {
   static const int m = [] { const char* e = getenv("MEMVUL_ATT_WAIT"); return e ? atoi(e) & 63 : 5; }();
-  return m;
+  // MEMVUL_ATT_STAGGER=<cycles> (bits 8..): the second CTA of every SM starts its soft-max stream that many cycles late, so
+  // that the two co-resident CTAs' exponentiation phases (MUFU-bound: 2 x 64 MUFU.EX2 per thread and key block on the one
+  // XU of a sub-partition) interleave instead of coinciding.  Both CTAs start together and run identical work, so without
+  // the offset they stay in phase for the whole launch (r01p trace: the exp phase takes 970 cycles, twice its solo time).
+  static const int stagger = [] { const char* e = getenv("MEMVUL_ATT_STAGGER"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 100000 ? 100000 : v); }();
+  // MEMVUL_ATT_EARLY (default 1, bit 8): the soft-max warps issue non-blocking mbarrier.test_wait for pv_done(g-1) and
+  // s_full(g+1) under the exponentials instead of paying two blocking try_wait round trips per key block
+  static const int early = [] { const char* e = getenv("MEMVUL_ATT_EARLY"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  // MEMVUL_ATT_SPEC (default 1, bit 9): speculative exponentials against the stale row maximum (attention_tcgen05.cuh)
+  static const int spec = [] { const char* e = getenv("MEMVUL_ATT_SPEC"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  return m | (early << 8) | (spec << 9) | (stagger << 10);
 }
 
 int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_start, void* ctx, int B, int S, int H,
@@ -421,7 +431,9 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   else { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
   const int n_items = B * (H / 64) * n_qt;
-  const int grid = n_items < 2 * di.sms ? n_items : 2 * di.sms;       // persistent: two CTAs per SM
+  // MEMVUL_ATT_CTAS_PER_SM=1: diagnostic (one CTA per SM: the soft-max phases without a co-resident CTA's MUFU traffic)
+  static const int ctas_per_sm = [] { const char* e = getenv("MEMVUL_ATT_CTAS_PER_SM"); return (e && atoi(e) == 1) ? 1 : 2; }();
+  const int grid = n_items < ctas_per_sm * di.sms ? n_items : ctas_per_sm * di.sms;       // persistent: two CTAs per SM
   // MEMVUL_ATT_TRACE=<file>: debug only -- CTA 0 records clock64() per soft-max / MMA phase (tools/att_trace.py)
   static const char* trace_path = getenv("MEMVUL_ATT_TRACE");
   static unsigned long long* trace_buf = nullptr;

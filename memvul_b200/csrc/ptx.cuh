@@ -56,6 +56,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test.  The result is scoreboarded like a load: issue it EARLY, keep computing, branch on it later.
+// A soft-max warp that loops on try_wait pays ~90-180 cycles per barrier even when the phase completed long ago
+// (B300_MICROARCH.md: TRYWAIT 90 cycles on the already-complete fast path); two such waits per key block were 340 of the
+// 1,590 cycles of the attention kernel's serial per-block chain (r02o trace).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // try_wait with a suspend-time hint: the hardware may park the thread for up to `ns` nanoseconds (it is released as
 // soon as the phase completes), so a single-lane role warp that waits for a long time does not burn the issue
 // slots of the compute warps sharing its scheduler with a tight SYNCS/BRA loop.

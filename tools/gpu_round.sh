@@ -3,7 +3,7 @@
 # then a short C2 bench.  Logs land in gpurun_out/<tag>_*.
 tag=${1:-run}
 mkdir -p gpurun_out
-for f in tests/test_packed_gpu.py tests/test_kernels_gpu.py tests/test_parity_gpu.py tests/test_configs_gpu.py; do
+for f in tests/test_packed_gpu.py tests/test_kernels_gpu.py tests/test_precise_gpu.py tests/test_parity_gpu.py tests/test_configs_gpu.py; do
   n=$(basename $f .py)
   timeout 900 python -m pytest $f -m gpu -q -s --timeout 600 > gpurun_out/${tag}_${n}.log 2>&1
   echo "$n rc=$?"; tail -3 gpurun_out/${tag}_${n}.log
