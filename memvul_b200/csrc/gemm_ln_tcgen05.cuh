@@ -42,7 +42,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                            const __grid_constant__ CUtensorMap tmap_x16, int M, int K, const float* __restrict__ bias,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int a_multicast,
                            const int* __restrict__ m_dev, unsigned long long* __restrict__ trace,
-                           float* __restrict__ x32_ptr, __half* __restrict__ x16_ptr, const float* resid_ptr) {
+                           float* __restrict__ x32_ptr, __half* __restrict__ x16_ptr, const float* resid_ptr, int pace) {
   using Cfg = GemmLnCfg;
   // debug only (MEMVUL_LN_TRACE): CTA 0 stamps clock64() at the phase boundaries of its first 8 tiles
   // (epilogue warp 0 slots 0-13, MMA warp slots 14-15; tools/ln_trace.py)
@@ -118,10 +118,24 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
+      // Paced producer (MEMVUL_LN_PACE = cycles between stage requests; experiment, default off).  At K = 768 the kernel
+      // is epilogue-bound (the MMA needs 6 k of a ~17.7 k-cycle tile period) and 8 k of those cycles are exposed residual
+      // waits (~3 k per box pair, through TMA and LDGSTS alike).  Hypothesis: the free-running producer's 64 B/clk burst
+      // for the next tile delays the residual boxes at the SM's L2 port.  Measured r02o (tools/gpu_ln_pace.sh): spreading
+      // the stage requests over the tile period (600 ... 1,100 cycles apart) leaves the residual waits at 2.5-4.4 k cycles
+      // and the kernel at 73.7-74.4 us; above 1,300 the MMA starves.  So the ~3 k cycles are the loaded memory-system
+      // latency of the box itself (DRAM at ~50 % utilisation with mixed reads / writes), and what is missing is bytes in
+      // flight for the residual (two 4 KB boxes per warp; shared memory is full), not request ordering.
+      long long next_issue = pace > 0 ? clock64() : 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int row_a = tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_idle(&empty_bar[stage], phase ^ 1u, idle_tma);
+          if (pace > 0) {
+            long long now = clock64();
+            while (now < next_issue) { __nanosleep(100); now = clock64(); }
+            next_issue = (now - next_issue > 4 * pace ? now : next_issue) + pace;     // never bank more than 4 stages of credit
+          }
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (issuer) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);

@@ -367,6 +367,9 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   // through the LSU path).  r02i: both wait ~3 k cycles per exposed box at K = 768 (and ~0.2 k with a 2-deep A/B ring that
   // starves the MMA): the latency is the SM's own queue of outstanding operand bytes at the L2 port, whichever unit asks.
   static const int res_ldgsts = [] { const char* e = getenv("MEMVUL_LN_RES"); return (e && strcmp(e, "ldgsts") == 0) ? 1 : 0; }();
+  // MEMVUL_LN_PACE=<cycles>: minimum spacing of the producer's stage requests for K <= 1024 (see the kernel)
+  static const int pace_short = [] { const char* e = getenv("MEMVUL_LN_PACE"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 20000 ? 20000 : v); }();
+  const int pace = K <= 1024 ? pace_short : 0;
   CUtensorMap ta, ta64, tb, tres, t32, t16;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, &ta)) return rc;
   if (int rc = make_map_f16(a, (uint64_t)M, (uint64_t)K, (uint64_t)K, 64, &ta64)) return rc;
@@ -383,7 +386,7 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 128 * 8, st));
   {
     LaunchScope ls(g_cls, st);
-    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4) | (ring << 12) | (res_ldgsts << 15), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16), resid);
+    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4) | (ring << 12) | (res_ldgsts << 15), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16), resid, pace);
     CUDA_TRY(cudaGetLastError());
   }
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
