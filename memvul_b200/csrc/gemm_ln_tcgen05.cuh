@@ -57,7 +57,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;                      // [EPI_WARPS][2]
   uint64_t* stats_bar = res_bar + 2 * Cfg::EPI_WARPS;      // [2 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stats_bar + 2);
+  uint64_t* xres_bar = stats_bar + 2;                      // [EPI_WARPS] third residual buffer (xbuf)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xres_bar + Cfg::EPI_WARPS);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
@@ -81,6 +82,14 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   // unit waits behind the four main-loop stages queued ahead of it (3.1 k + 4.1 k exposed cycles per tile at K = 768; 0.2 k
   // with a 2-deep ring, which starves the MMA instead) -- the LSU path has its own queue
   const bool res_ldgsts = ((a_multicast >> 15) & 1) != 0;
+  // Third residual buffer per epilogue warp (r02o).  The exposed residual-box latency (~3 k cycles per pair of boxes, 8 k
+  // of a 17.7 k-cycle tile period at K = 768) is the loaded memory-system latency of the boxes, and the two 4 KB buffers
+  // per warp double as the TMA-store staging of pass 2, so the next tile's boxes can only be requested when this tile is
+  // done.  A short-K problem does not need the fourth A/B stage (ring 3 measured equal), whose 32 KB become one extra 4 KB
+  // buffer per warp that is NEVER used for staging: chunk 0 of the next tile is requested into it at the start of pass 2
+  // (a whole pass ahead: it lands hidden), chunks 1 and 2 go to the old pair at the end of the tile, chunk 3 follows
+  // chunk 0 into the extra buffer.  Three boxes instead of two are in flight when pass 1 begins.
+  const bool xbuf = ((a_multicast >> 16) & 1) != 0 && nstages <= 3 && !direct_st && !res_ldgsts;
   a_multicast &= 1;
 
   if (warp_idx == 0 && lane == 0) {
@@ -94,6 +103,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&res_bar[i], res_ldgsts ? 32 : 1);   // one arrival per lane / one expect_tx
     // classic exchange: 3 CTAs x 8 warps arrive; st.async exchange: one local expect_tx arrival + 6,144 bytes of complete_tx
     for (int i = 0; i < 2; ++i) mbar_init(&stats_bar[i], async_stats ? 1 : Cfg::PAIRS * Cfg::EPI_WARPS);
+    for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(&xres_bar[i], 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -203,6 +213,17 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     uint8_t* buf0 = smem + Cfg::OFF_STG + ew * 2 * Cfg::STG_BYTES;       // residual ping / fp32 output staging
     uint8_t* buf1 = buf0 + Cfg::STG_BYTES;                               // residual pong / fp16 output staging
     uint64_t* my_res_bar = res_bar + 2 * ew;
+    uint8_t* bufc = smem + 3 * Cfg::STAGE_BYTES + ew * Cfg::STG_BYTES;   // xbuf: this warp's slice of the unused fourth A/B stage
+    uint64_t* my_xbar = xres_bar + ew;
+    // chunk c of a tile -> residual buffer / its barrier.  Classic: ping-pong (c & 1).  xbuf: 0 -> C, 1 -> A, 2 -> B, 3 -> C.
+    auto chunk_buf = [&](int c) -> uint8_t* {
+      if (!xbuf) return (c & 1) ? buf1 : buf0;
+      return (c == 0 || c == 3) ? bufc : (c == 1 ? buf0 : buf1);
+    };
+    auto chunk_bar = [&](int c) -> uint64_t* {
+      if (!xbuf) return &my_res_bar[c & 1];
+      return (c == 0 || c == 3) ? my_xbar : &my_res_bar[c - 1];
+    };
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const int col0 = static_cast<int>(pair) * Cfg::BN + half_sel * 128;  // first of this warp's 128 columns
     const int row_in_cta = quarter * 32 + lane;
@@ -216,7 +237,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 
     auto strip_row0 = [&](int tile) { return tile * Cfg::BM + static_cast<int>(half_m) * Cfg::BM_CTA + quarter * 32; };
     auto issue_res = [&](int tile, int c) {                 // residual box (rows of `tile`, chunk c) -> buffer c & 1
-      uint8_t* dst = (c & 1) ? buf1 : buf0;
+      uint8_t* dst = chunk_buf(c);
       if (res_ldgsts) {
         // whole warp: lane -> (row lane/8 + 4 i, 16-byte unit lane%8); four full 128 B lines per instruction, written to
         // the positions a SWIZZLE_128B TMA box would use
@@ -231,11 +252,11 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         }
         cp_async_mbar_arrive(&my_res_bar[c & 1]);
       } else if (lane == 0) {
-        mbar_arrive_expect_tx(&my_res_bar[c & 1], Cfg::STG_BYTES);
-        tma_load_2d(dst, &tmap_res, &my_res_bar[c & 1], col0 + c * 32, strip_row0(tile), kEvictFirst);
+        mbar_arrive_expect_tx(chunk_bar(c), Cfg::STG_BYTES);
+        tma_load_2d(dst, &tmap_res, chunk_bar(c), col0 + c * 32, strip_row0(tile), kEvictFirst);
       }
     };
-    if (cluster_id < num_tiles) { issue_res(cluster_id, 0); issue_res(cluster_id, 1); }
+    if (cluster_id < num_tiles) { issue_res(cluster_id, 0); issue_res(cluster_id, 1); if (xbuf) issue_res(cluster_id, 2); }
 
     int acc = 0;
     uint32_t acc_phase = 0, gc = 0, it = 0;
@@ -265,8 +286,11 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         tmem_wait_ld();
         if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&a)[32] = r[c & 1];
-        uint8_t* rowp = ((c & 1) ? buf1 : buf0) + lane * 128;
-        mbar_wait_idle(&my_res_bar[c & 1], (gc >> 1) & 1u, idle_epi);
+        uint8_t* rowp = chunk_buf(c) + lane * 128;
+        // n-th use of a barrier waits for parity n & 1.  Classic: each of the two barriers serves every other chunk.
+        // xbuf: A / B serve one chunk per tile, C two (chunk 0: even use, chunk 3: odd use).
+        const uint32_t res_parity = !xbuf ? ((gc >> 1) & 1u) : ((c == 0) ? 0u : (c == 3 ? 1u : (it & 1u)));
+        mbar_wait_idle(chunk_bar(c), res_parity, idle_epi);
         ++gc;
         if (tr) stamp(it, 2 + c);
         uint32_t v[32];
@@ -285,12 +309,14 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         }
         tmem_st_32x32b_x32(t_addr + c * 32, v);            // stash for pass 2
         __syncwarp();                                      // every lane has read this residual buffer
-        if (c + 2 < NCHUNK) issue_res(tile, c + 2);
+        if (!xbuf) { if (c + 2 < NCHUNK) issue_res(tile, c + 2); }
+        else if (c == 0) issue_res(tile, 3);                // chunk 3 follows chunk 0 into the extra buffer
       }
       // ---------------- exchange the row statistics with the two other column blocks ----------------
       if (tr) stamp(it, 6);
       const uint32_t slot = it & 1u;
       const int next_tile = tile + num_clusters;
+      if (xbuf && next_tile < num_tiles) issue_res(next_tile, 0);   // extra buffer is free: a whole pass 2 ahead of its use
       if (direct_st && next_tile < num_tiles) {
         // both residual buffers are free (pass 2 does not stage): request the next tile's first two chunks now, a whole
         // exchange + pass 2 ahead of their use, and pull its last two chunks into L2
@@ -405,7 +431,10 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       }
       if (!direct_st) {
         __syncwarp();
-        if (next_tile < num_tiles) { issue_res(next_tile, 0); issue_res(next_tile, 1); }
+        if (next_tile < num_tiles) {
+          if (xbuf) { issue_res(next_tile, 1); issue_res(next_tile, 2); }
+          else { issue_res(next_tile, 0); issue_res(next_tile, 1); }
+        }
       }
       if (tr) stamp(it, 13);
       acc ^= 1;

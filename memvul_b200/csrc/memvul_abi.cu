@@ -362,7 +362,11 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   static const int ln_mode = [] { const char* e = getenv("MEMVUL_LN_MODE"); return e ? atoi(e) & 7 : 2; }();
   // MEMVUL_LN_RING_SHORT: A/B ring depth (2..4) for K <= 1024 (see the kernel); longer K always uses all four stages
   static const int ring_short = [] { const char* e = getenv("MEMVUL_LN_RING_SHORT"); int v = e ? atoi(e) : 4; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
-  const int ring = K <= 1024 ? ring_short : 4;
+  // MEMVUL_LN_XBUF (default 1): for K <= 1024 the fourth A/B stage becomes a third residual buffer per epilogue warp (kernel
+  // comment); implies a ring of at most three stages
+  static const int xbuf_on = [] { const char* e = getenv("MEMVUL_LN_XBUF"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  const int xbuf = (K <= 1024 && xbuf_on && !(ln_mode & 1)) ? 1 : 0;
+  const int ring = K <= 1024 ? (xbuf && ring_short > 3 ? 3 : ring_short) : 4;
   // MEMVUL_LN_RES: how the epilogue fetches the fp32 residual boxes: "tma" (default) or "ldgsts" (per-lane cp.async
   // through the LSU path).  r02i: both wait ~3 k cycles per exposed box at K = 768 (and ~0.2 k with a 2-deep A/B ring that
   // starves the MMA): the latency is the SM's own queue of outstanding operand bytes at the L2 port, whichever unit asks.
@@ -386,7 +390,7 @@ int gemm_ln_impl(const void* a, const void* w, const float* bias, const float* r
   if (trace_buf) CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 128 * 8, st));
   {
     LaunchScope ls(g_cls, st);
-    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4) | (ring << 12) | (res_ldgsts << 15), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16), resid, pace);
+    kern<<<Cfg::CLUSTER * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta64, tb, tres, t32, t16, M, K, bias, gamma, beta, eps, (a_mc ? 1 : 0) | (ln_mode << 1) | (gemm_wait_mode() << 4) | (ring << 12) | (res_ldgsts << 15) | (xbuf << 16), m_dev, trace_buf, x32, reinterpret_cast<__half*>(x16), resid, pace);
     CUDA_TRY(cudaGetLastError());
   }
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch
