@@ -35,7 +35,11 @@ template <int EPI>
 struct Gemm2Cfg {
   static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
   static constexpr int BM = 256, BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64;
-  static constexpr int STAGES = RESID ? 4 : 5;            // measured: 3 stages starve the K=3072 main loop
+#ifndef MV_GEMM_RESID_STAGES
+#define MV_GEMM_RESID_STAGES 4    // experiment (r02o): 5 = five A/B stages for the residual epilogue too, paid for with ONE
+                                  // staging buffer per epilogue warp (serialised residual load -> add -> store)
+#endif
+  static constexpr int STAGES = RESID ? MV_GEMM_RESID_STAGES : 5;            // measured: 3 stages starve the K=3072 main loop
   static constexpr int A_BYTES = BM_CTA * BK * 2;          // 16 KB
   static constexpr int B_BYTES = BN_CTA * BK * 2;          // 16 KB (half of the tile's B rows)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB per CTA
@@ -46,7 +50,7 @@ struct Gemm2Cfg {
   // RESID: ping-pong, next residual box in flight.  fp16 outputs: ping-pong too (MV_GEMM_STG2) -- the TMA unit serves an
   // SM's requests in order, so an output box queues behind every main-loop stage in flight (~2.5 k cycles) and a warp
   // that must see its single staging buffer drained before packing the next box spends the epilogue waiting
-  static constexpr int STG_BUFS = (RESID || MV_GEMM_STG2) ? 2 : 1;
+  static constexpr int STG_BUFS = ((RESID && MV_GEMM_RESID_STAGES < 5) || MV_GEMM_STG2) ? 2 : 1;
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;
   // bias slices: a private 128-float copy per epilogue warp (the warps are not in lock step across tiles).  With two
   // fp16 staging buffers the 4 KB no longer fit next to five main-loop stages; those epilogues read the bias through
@@ -201,7 +205,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
     auto issue_res_load = [&](uint32_t q) {
       const int t = cluster_id + static_cast<int>(q / NCHUNK) * num_clusters;
       if (t < num_tiles) {
-        const uint32_t nb = q & 1u;
+        const uint32_t nb = Cfg::STG_BUFS == 2 ? (q & 1u) : 0u;
         mbar_arrive_expect_tx(&my_res_bar[nb], Cfg::STG_BYTES);
         tma_load_2d(my_stg + nb * Cfg::STG_BYTES, &tmap_res, &my_res_bar[nb], strip_col0(t) + static_cast<int>(q % NCHUNK) * 32,
                     strip_row0(t), kEvictFirst);
@@ -213,7 +217,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
     if constexpr (Cfg::RESID) {
       if (lane == 0 && store && !no_resid) {
         issue_res_load(0);
-        issue_res_load(1);
+        if (Cfg::STG_BUFS == 2) issue_res_load(1);
       }
     }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -236,10 +240,10 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         const uint32_t(&v)[32] = r[c & 1];
         const float* bsm = Cfg::BIAS_SMEM ? my_bias + c * 32 : bias + col0 + c * 32;
         if constexpr (Cfg::RESID) {
-          const uint32_t b = gc & 1u;
+          const uint32_t b = Cfg::STG_BUFS == 2 ? (gc & 1u) : 0u;
           uint8_t* rowp = my_row0 + b * Cfg::STG_BYTES;
           if (store) {
-            if (!no_resid) mbar_wait_idle(&my_res_bar[b], (gc >> 1) & 1u, idle_epi);   // residual chunk has landed
+            if (!no_resid) mbar_wait_idle(&my_res_bar[b], (Cfg::STG_BUFS == 2 ? (gc >> 1) : gc) & 1u, idle_epi);   // residual chunk has landed
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               float4* p = reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(u) ^ sw) << 4));
@@ -258,7 +262,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
               tma_store_2d(&tmap_out, my_stg + b * Cfg::STG_BYTES, col0 + c * 32, row0);
               bulk_commit_group();
               bulk_wait_read_all();                // this store has left the buffer: refill it with chunk gc+2
-              if (!no_resid) issue_res_load(gc + 2);
+              if (!no_resid) issue_res_load(gc + Cfg::STG_BUFS);
             }
           }
           ++gc;
