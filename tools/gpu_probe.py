@@ -10,7 +10,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["gemm", "gemm_ln", "attention", "rowwise", "poolmatch", "encoder_tiny", "encoder_base", "model"]
+GROUPS = ["gemm", "gemm_ln", "attention", "rowwise", "poolmatch", "encoder_tiny", "encoder_base", "model", "precise"]
 
 
 def _report(name, got, ref, tol):
@@ -259,6 +259,42 @@ def g_encoder_tiny():
 def g_encoder_base():
     from oracle import memvul_oracle as O
     return _encoder(O.BERT_BASE, 4, 128, [128, 100, 64, 17], 1.5e-2) & _encoder(O.BERT_BASE, 2, 512, [512, 300], 1.5e-2)
+
+
+def g_precise():
+    """Accuracy mode (MEMVUL_ENC_PRECISE) building blocks and the tiny encoder, padded and packed; also the default packed
+    encoder (speculative-softmax attention, third-residual-buffer GEMM+LN at M >= 256)."""
+    import torch
+    from memvul_b200 import native as N
+    from oracle import memvul_oracle as O
+    ok = True
+    torch.manual_seed(3)
+    x = torch.randn(300, 768, device="cuda")
+    sp = N.split3_f16(x)
+    ok &= _report("split3 hi+lo", sp[:, :768].float() + sp[:, 768:1536].float(), x, 1e-6)
+    w = torch.randn(768, 768, device="cuda") * 0.05
+    bias = torch.randn(768, device="cuda")
+    out = N.gemm_f16(sp, N.split3_weight(w), bias, N.EPI_BIAS_F32)
+    ok &= _report("split GEMM 300x768x768 (fp32 out, no residual)", out, x @ w.T + bias, 1e-4)
+    qkv = torch.randn(2 * 200, 3 * 128, device="cuda")
+    lens = torch.tensor([200, 77], dtype=torch.int32, device="cuda")
+    ctx = N.attention_f32(qkv, lens, 2, 200, 128)
+    ref, valid = _attn_ref(qkv, lens, 2, 200, 128)
+    valid = valid.reshape(-1)
+    ok &= _report("attention_f32 B=2 S=200", ctx[valid], ref[valid], 1e-4)
+    sd = O.synthetic_state_dict(O.BERT_TINY)
+    ids, mask, tids = O.synthetic_ids(3, 300, lens=[300, 131, 17], vocab_size=O.BERT_TINY.vocab_size)
+    refh = O.bert_encoder(sd, ids, mask.float(), None, O.BERT_TINY)
+    for precise in (True, False):
+        wts = N.PackedBert(sd, O.EMB, torch.device("cuda"), precise=precise)
+        for packed in (False, True):
+            if packed:
+                lens_t, rs, bad = N.mask_to_lens(mask.cuda(), with_row_start=True)
+            else:
+                (lens_t, bad), rs = N.mask_to_lens(mask.cuda()), None
+            hid = N.encoder_forward(wts, ids.cuda(), lens_t, row_start=rs, bad=bad)
+            ok &= _report(f"encoder tiny precise={precise} packed={packed}", hid.cpu()[mask], refh[mask], 2e-5 if precise else 2e-2)
+    return ok
 
 
 def g_model():
