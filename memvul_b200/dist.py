@@ -144,3 +144,33 @@ def gather_match_flat(result: Dict[str, torch.Tensor], counts: Sequence[int],
     ag.submit(result)
     parts = ag.wait()
     return {k: torch.cat(v) for k, v in parts.items()}
+
+
+def build_memory_sharded(model, golden_instances: Sequence, chunk: int = 128,
+                         group: Optional[dist.ProcessGroup] = None) -> None:
+    """the anchor memory of a multi-GPU job is built ONCE -- rank r encodes its contiguous slice of the
+    golden instances (in the reference's chunks of 128, predict_memory.py:79-83) and one all-gather of the
+    ``[G_r, 512]`` rows gives every rank the whole bank, in file order, with the labels of ALL anchors.  For the
+    16,384-anchor stress bank that is 1/world of the 1.58 PFLOP a replicated build costs; rows are bit-identical to a
+    single-process build made with the same chunk boundaries inside each slice (every row depends on its own anchor only).
+    ``model``: a ``ModelMemory`` (anything with ``forward_on_instances`` filling ``_golden_instances_embeddings`` /
+    ``_golden_instances_labels``)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = shard_bounds(len(golden_instances), world)
+    counts = [e - s for s, e in bounds]
+    if min(counts) == 0:
+        raise ValueError(f"build_memory_sharded needs at least one golden instance per rank ({len(golden_instances)} over {world})")
+    s, e = bounds[rank]
+    model._golden_instances_embeddings = None
+    model._golden_instances_labels = None
+    for c0 in range(s, e, chunk):
+        model.forward_on_instances(list(golden_instances[c0:min(e, c0 + chunk)]))
+    local = model._golden_instances_embeddings
+    local_labels = list(model._golden_instances_labels)
+    if local is None or local.shape[0] != counts[rank] or len(local_labels) != counts[rank]:
+        raise RuntimeError("build_memory_sharded: the model did not record one bank row per golden instance")
+    bank = gather_rows(local.contiguous(), counts, group)
+    labels: List[Optional[List[str]]] = [None] * world
+    dist.all_gather_object(labels, local_labels, group=group)          # a few KB of CWE ids, once per job
+    model._golden_instances_embeddings = bank                          # the setter drops the cached anchor-side match term
+    model._golden_instances_labels = [x for part in labels for x in part]

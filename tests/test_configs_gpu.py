@@ -180,9 +180,20 @@ def _nccl_worker(rank, world, port, q):
             torch.cuda.synchronize()
             got = {k: torch.cat(v) for k, v in parts.items()}
             old = gather_match(model.match_batch(sh), counts, full=True)          # the packed-copy form gives the same
+            # rank-sharded bank build (each rank encodes its slice, ONE all-gather of the rows) == the bank every
+            # rank built for itself above (same chunking inside the slices: 5 anchors -> 3 + 2)
+            from memvul_b200.dist import build_memory_sharded
+            bank_full, labels_full = model._golden_instances_embeddings.clone(), list(model._golden_instances_labels)
+            golden = [{"sample1": {"token_ids": a_ids[i][:alens[i]].tolist(), "type_ids": [0] * alens[i]}, "label": None,
+                       "metadata": {"type": "golden", "instance": [{"label": f"CWE-{i}"}]}} for i in range(5)]
+            build_memory_sharded(model, golden)
+            bank_ok = (model._golden_instances_labels == labels_full
+                       and float((model._golden_instances_embeddings - bank_full).abs().max()) < 1e-5)
+            again = model.match_batch({"tokens": {"token_ids": to(ids), "mask": to(mask), "type_ids": to(tids)}})
+            bank_ok = bank_ok and float((again["logits"] - whole["logits"]).abs().max()) < 1e-5
         ok = (torch.equal(got["probs"], whole["probs"]) and torch.equal(got["best_idx"], whole["best_idx"])
               and torch.equal(got["best_probs"], whole["best_probs"]) and torch.equal(old["probs"], whole["probs"])
-              and torch.equal(old["best_idx"], whole["best_idx"]))
+              and torch.equal(old["best_idx"], whole["best_idx"]) and bank_ok)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from memvul_b200.dist import balanced_assignment, gather_match, gather_rows, shard_bounds
+from memvul_b200.dist import balanced_assignment, build_memory_sharded, gather_match, gather_rows, shard_bounds
 
 
 def test_shard_bounds_cover_and_balance():
@@ -63,3 +63,51 @@ def test_gather_match_world2_gloo():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
+
+
+class _StubMemoryModel:
+    """The two attributes and one method of ModelMemory that the sharded bank build touches; 'encoding' an anchor is a
+    deterministic function of the anchor alone, like the real encoder."""
+
+    def __init__(self):
+        self._golden_instances_embeddings = None
+        self._golden_instances_labels = None
+        self.calls = []
+
+    def forward_on_instances(self, instances):
+        self.calls.append(len(instances))
+        rows = torch.stack([torch.full((4,), float(i["id"])) + torch.arange(4.0) / 10 for i in instances])
+        labels = [i["label"] for i in instances]
+        if self._golden_instances_embeddings is None:
+            self._golden_instances_embeddings, self._golden_instances_labels = rows, labels
+        else:
+            self._golden_instances_embeddings = torch.cat([self._golden_instances_embeddings, rows])
+            self._golden_instances_labels = self._golden_instances_labels + labels
+
+
+def _bank_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        golden = [{"id": i, "label": f"CWE-{i % 5}"} for i in range(11)]            # ragged: 6 + 5 anchors
+        single = _StubMemoryModel()
+        single.forward_on_instances(golden)
+        m = _StubMemoryModel()
+        m._golden_instances_embeddings = torch.zeros(3, 4)                              # a stale bank must be replaced
+        build_memory_sharded(m, golden, chunk=4)
+        assert torch.equal(m._golden_instances_embeddings, single._golden_instances_embeddings)
+        assert m._golden_instances_labels == single._golden_instances_labels
+        assert m.calls == ([4, 2] if rank == 0 else [4, 1])                             # own slice only, in chunks
+        with pytest.raises(ValueError):
+            build_memory_sharded(_StubMemoryModel(), golden[:1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_build_memory_sharded_world2_gloo():
+    """rank-sharded anchor encoding + one all-gather of the bank rows == the single-process bank."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_bank_worker, args=(2, port), nprocs=2, join=True)
