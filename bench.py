@@ -45,6 +45,10 @@ sys.path.insert(0, ROOT)
 
 SEQ, SEED = 512, 2021
 METRIC, UNIT = "issue-reports/sec, bert-base seq512 + CWE memory", "issues/s"
+# which attention kernel the C ABI launches (memvul_abi.cu: MEMVUL_ATT_V, default 3)
+ATT_KERNEL = {"1": "attention_tcgen05_kernel", "2": "attention_tcgen05_v2_kernel"}.get(
+    os.environ.get("MEMVUL_ATT_V", "3"), "attention_tcgen05_v3_kernel<%s>" % os.environ.get("MEMVUL_ATT_POLY", "0"))
+
 CONFIGS = {
     "c2": {"B": 64, "G": 129, "lens": "full", "name": "C2 predict_memory: bert-base S=512, 64 issue reports/GPU, 129-anchor CWE memory"},
     "c3": {"B": 128, "G": 129, "lens": "full", "name": "C3 predict_memory: bert-base S=512, 128 issue reports/GPU (1024 over 8 GPUs), 129 anchors"},
@@ -462,7 +466,7 @@ def run_native(args):
     step_ms_prof = sum(v["ms"] for v in prof.values()) / prof_steps
     kernels = {}
     kname = {"embed_ln": "embed_layernorm_kernel", "gemm_qkv": "gemm_f16_tcgen05_2cta_kernel<BIAS_F16>",
-             "attention": "attention_tcgen05_kernel", "attention_cls": "attention_tcgen05_kernel (first query tile, last layer)",
+             "attention": ATT_KERNEL, "attention_cls": ATT_KERNEL + " (first query tile, last layer)",
              "gemm_attn_out": "gemm_ln_f16_tcgen05_kernel (K=768)", "gemm_ffn_up": "gemm_f16_tcgen05_2cta_kernel<BIAS_GELU_F16>",
              "gemm_ffn_down": "gemm_ln_f16_tcgen05_kernel (K=3072)", "cls_tail": "gemm_f16_tcgen05_kernel<128,*> + layernorm_rows (B rows)",
              "pool_match": "pool_match_kernel", "layernorm": "layernorm_rows_kernel", "other": "mask_to_lens / row_start / gather_cls"}

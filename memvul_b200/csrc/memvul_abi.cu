@@ -15,6 +15,7 @@
 #include "../../include/memvul_b200.h"
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_v2.cuh"
+#include "attention_tcgen05_v3.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "gemm_ln_tcgen05.cuh"
@@ -432,14 +433,26 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   // MEMVUL_ATT_V=2 selects the experimental second-generation kernel (attention_tcgen05_v2.cuh: 8 soft-max warps splitting
   // every row, separate Q K^T / P V issuers, double-buffered O).  It is parity-green but measured SLOWER (r02e: 133.7 us
   // against 116.3 us at 64 x 512): the block period is set by the MUFU phase all warps of a CTA enter together, not by
-  // the per-thread chain that the split shortens.  Default: the first-generation kernel.
-  static const bool v1 = [] { const char* e = getenv("MEMVUL_ATT_V"); return !(e && atoi(e) == 2); }();
+  // the per-thread chain that the split shortens.
+  // Default (MEMVUL_ATT_V unset or 3): the three-streams-per-SM kernel (attention_tcgen05_v3.cuh: 3 CTAs per SM, soft-max
+  // warps on 120 registers by setmaxnreg, single-buffered S / P, separate K / V rings; r02q: 106.9 against 115.8 us at
+  // 64 x 512, 69.9 against 80.3 at 128 x 256, bit-identical results).  MEMVUL_ATT_V=1: the first kernel (two CTAs per SM).
+  // MEMVUL_ATT_POLY=2: two of every 8 exponentials of the v3 kernel on the FMA pipe (measured slower, 111.5 us: the MUFU
+  // pipe is not the limiter even with three streams).
+  static const int att_v = [] { const char* e = getenv("MEMVUL_ATT_V"); int v = e ? atoi(e) : 3; return (v == 1 || v == 2) ? v : 3; }();
+  static const int att_poly = [] { const char* e = getenv("MEMVUL_ATT_POLY"); return (e && atoi(e) == 2) ? 2 : 0; }();
+  const bool v1 = att_v == 1;
+  const void* v3_fn = att_poly == 2 ? reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<2>)
+                                    : reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<0>);
   if (v1) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc; }
-  else { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
+  else if (att_v == 2) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
+  else { if (int rc = ensure_dyn_smem(v3_fn, mv::Attn3Cfg::SMEM_BYTES)) return rc; }
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
   const int n_items = B * (H / 64) * n_qt;
   // MEMVUL_ATT_CTAS_PER_SM=1: diagnostic (one CTA per SM: the soft-max phases without a co-resident CTA's MUFU traffic)
-  static const int ctas_per_sm = [] { const char* e = getenv("MEMVUL_ATT_CTAS_PER_SM"); return (e && atoi(e) == 1) ? 1 : 2; }();
+  static const int ctas_env = [] { const char* e = getenv("MEMVUL_ATT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const int ctas_max = att_v == 3 ? mv::Attn3Cfg::CTAS_PER_SM : 2;
+  const int ctas_per_sm = (ctas_env >= 1 && ctas_env <= ctas_max) ? ctas_env : ctas_max;
   const int grid = n_items < ctas_per_sm * di.sms ? n_items : ctas_per_sm * di.sms;       // persistent: two CTAs per SM
   // MEMVUL_ATT_TRACE=<file>: debug only -- CTA 0 records clock64() per soft-max / MMA phase (tools/att_trace.py)
   static const char* trace_path = getenv("MEMVUL_ATT_TRACE");
@@ -453,9 +466,15 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
     if (v1)
       mv::attention_tcgen05_kernel<<<grid, mv::AttnCfg::THREADS, mv::AttnCfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
-    else
+    else if (att_v == 2)
       mv::attention_tcgen05_v2_kernel<<<grid, mv::Attn2Cfg::THREADS, mv::Attn2Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+    else if (att_poly == 2)
+      mv::attention_tcgen05_v3_kernel<2><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
+    else
+      mv::attention_tcgen05_v3_kernel<0><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
     CUDA_TRY(cudaGetLastError());
   }
   if (trace_buf) {                                  // debug: dump CTA 0's phase stamps of THIS launch

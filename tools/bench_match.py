@@ -56,6 +56,8 @@ def run_case(B, G, iters=20, phase=None):
 
 if __name__ == "__main__":
     cases = [(1, 262144), (2, 262144), (4, 262144), (4, 65536), (8, 65536), (256, 16384), (64, 129)]
+    if "--c4" in sys.argv:
+        cases = [(256, 16384), (1024, 16384)]
     for B, G in cases:
         for ph in (None, N.PM_UTERM | N.PM_MATCH | N.PM_FINAL):
             d = run_case(B, G, phase=ph)
