@@ -16,6 +16,7 @@
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_v2.cuh"
 #include "attention_tcgen05_v3.cuh"
+#include "attention_tcgen05_v4.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "gemm_ln_tcgen05.cuh"
@@ -439,16 +440,20 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   // 64 x 512, 69.9 against 80.3 at 128 x 256, bit-identical results).  MEMVUL_ATT_V=1: the first kernel (two CTAs per SM).
   // MEMVUL_ATT_POLY=2: two of every 8 exponentials of the v3 kernel on the FMA pipe (measured slower, 111.5 us: the MUFU
   // pipe is not the limiter even with three streams).
-  static const int att_v = [] { const char* e = getenv("MEMVUL_ATT_V"); int v = e ? atoi(e) : 3; return (v == 1 || v == 2) ? v : 3; }();
+  static const int att_v = [] { const char* e = getenv("MEMVUL_ATT_V"); int v = e ? atoi(e) : 3; return (v == 1 || v == 2 || v == 4) ? v : 3; }();
+  // MEMVUL_ATT_V=4: two query tiles per CTA in explicit ping-pong (attention_tcgen05_v4.cuh); MEMVUL_ATT4_TOKEN=0 lets its
+  // two contexts run free (diagnostic: what the token itself is worth)
+  static const int att4_token = [] { const char* e = getenv("MEMVUL_ATT4_TOKEN"); return (e && atoi(e) == 0) ? 0 : 1; }();
   static const int att_poly = [] { const char* e = getenv("MEMVUL_ATT_POLY"); return (e && atoi(e) == 2) ? 2 : 0; }();
   const bool v1 = att_v == 1;
   const void* v3_fn = att_poly == 2 ? reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<2>)
                                     : reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<0>);
   if (v1) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc; }
   else if (att_v == 2) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
+  else if (att_v == 4) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v4_kernel), mv::Attn4Cfg::SMEM_BYTES)) return rc; }
   else { if (int rc = ensure_dyn_smem(v3_fn, mv::Attn3Cfg::SMEM_BYTES)) return rc; }
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
-  const int n_items = B * (H / 64) * n_qt;
+  const int n_items = B * (H / 64) * (att_v == 4 ? (n_qt + 1) / 2 : n_qt);      // v4: an item is a PAIR of query tiles
   // MEMVUL_ATT_CTAS_PER_SM=1: diagnostic (one CTA per SM: the soft-max phases without a co-resident CTA's MUFU traffic)
   static const int ctas_env = [] { const char* e = getenv("MEMVUL_ATT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const int ctas_max = att_v == 3 ? mv::Attn3Cfg::CTAS_PER_SM : 2;
@@ -469,6 +474,9 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
     else if (att_v == 2)
       mv::attention_tcgen05_v2_kernel<<<grid, mv::Attn2Cfg::THREADS, mv::Attn2Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
+    else if (att_v == 4)
+      mv::attention_tcgen05_v4_kernel<<<grid, mv::Attn4Cfg::THREADS, mv::Attn4Cfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), att4_token);
     else if (att_poly == 2)
       mv::attention_tcgen05_v3_kernel<2><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());

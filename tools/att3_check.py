@@ -34,6 +34,7 @@ def main():
     cases = [(1, 128, 128, [128], False), (2, 128, 128, [128, 77], False), (2, 256, 128, [256, 130], False),
              (3, 512, 768, [512, 300, 5], False), (2, 200, 768, [200, 129], False), (4, 64, 128, [64, 2, 33, 17], False),
              (8, 512, 768, [512] * 8, False), (1, 1, 128, [1], False), (2, 512, 128, [511, 512], False),
+             (3, 384, 128, [384, 200, 129], False), (4, 384, 768, [384, 257, 256, 1], True), (2, 320, 128, [320, 127], False),
              (5, 512, 128, [512, 1, 130, 64, 300], True), (6, 511, 128, [257, 511, 129, 63, 200, 31], True),
              (40, 512, 768, [512, 77, 300, 128, 129] * 8, True), (64, 512, 768, [512] * 64, False)]
     for (B, S, H, lens, packed) in cases:
