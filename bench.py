@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 SEQ, SEED = 512, 2021
 METRIC, UNIT = "issue-reports/sec, bert-base seq512 + CWE memory", "issues/s"
 # which attention kernel the C ABI launches (memvul_abi.cu: MEMVUL_ATT_V, default 3)
-ATT_KERNEL = {"1": "attention_tcgen05_kernel", "2": "attention_tcgen05_v2_kernel", "4": "attention_tcgen05_v4_kernel"}.get(
+ATT_KERNEL = {"1": "attention_tcgen05_kernel", "2": "attention_tcgen05_v2_kernel"}.get(
     os.environ.get("MEMVUL_ATT_V", "3"), "attention_tcgen05_v3_kernel<%s>" % os.environ.get("MEMVUL_ATT_POLY", "0"))
 
 CONFIGS = {

@@ -45,7 +45,7 @@ struct Attn3Cfg {
   static constexpr int CTAS_PER_SM = 3;
   static constexpr int REGS_LAUNCH = 80, REGS_SOFTMAX = 120, REGS_AUX = 40;
   static_assert(REGS_SOFTMAX + REGS_AUX == 2 * REGS_LAUNCH, "the register pool of a CTA must balance");
-  static constexpr int TMEM_COLS = 128;
+  static constexpr int TMEM_COLS = 128, TMEM_COLS_P = 32;
   static constexpr int TM_S = 0, TM_O = 64;
 };
 
@@ -64,7 +64,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^n (n's integer bits sit at the bottom of t)
 }
 
-template <int POLY>
+template <int POLY, bool PTMEM>
 __global__ void __launch_bounds__(Attn3Cfg::THREADS, Attn3Cfg::CTAS_PER_SM)
 attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
                             const __grid_constant__ CUtensorMap tmap_ctx,
@@ -90,7 +90,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const 
   uint64_t* p_full = s_free + 1;                     // [1]  P_g in smem, O rescaled                   (4 warp arrivals)
   uint64_t* pv_done = p_full + 1;                    // [1]  P_g V_g accumulated into O
   uint64_t* o_free = pv_done + 1;                    // [1]  O of the previous item read out           (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);   // [0] S | O (128 columns), [1] P (32 columns, PTMEM only)
 
   if (warp_idx == 4) {
     if (lane == 0) {
@@ -114,12 +114,14 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const 
     }
     __syncwarp();
     tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (PTMEM) tmem_alloc(tmem_slot + 1, C::TMEM_COLS_P);    // 3 x (128 + 32) = 480 of the SM's 512 columns
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_p = PTMEM ? tmem_slot[1] : 0u;        // P as the TMEM A operand of O += P V (fp16 pairs, 32 columns)
 
   // Every role walks the same item sequence; `g` counts key blocks and `it` non-skipped items over the CTA's life.  All
   // single-buffered barriers complete one phase per key block (parity g & 1), the two-stage rings one per two blocks.
@@ -215,8 +217,11 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const 
             // A = P: K-major 64-wide chunk, 32 B per K=16 step.  B = V: N-major (one 128 B swizzle row per key),
             // 16 keys = 2048 B per step.
             const uint64_t b_desc = umma_desc_sw128(v_addr + kk * 2048);
-            umma_f16_ss(tmem_base + C::TM_O, p_desc + static_cast<uint64_t>(kk * 2), b_desc, idesc_pv,
-                        (j | kk) != 0 ? 1u : 0u);
+            if (PTMEM)
+              umma_f16_ts(tmem_base + C::TM_O, tmem_p + static_cast<uint32_t>(kk * 8), b_desc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            else
+              umma_f16_ss(tmem_base + C::TM_O, p_desc + static_cast<uint64_t>(kk * 2), b_desc, idesc_pv,
+                          (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(pv_done);
           umma_commit(&v_empty[st]);
@@ -348,10 +353,26 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const 
           }
         }
 #pragma unroll
-        for (int unit = 0; unit < 8; ++unit) *reinterpret_cast<uint4*>(p_row + ((unit ^ (r & 7)) << 4)) = pk[unit];
+        for (int unit = 0; unit < 8; ++unit)
+          if (!PTMEM) *reinterpret_cast<uint4*>(p_row + ((unit ^ (r & 7)) << 4)) = pk[unit];
+        if (PTMEM) {
+          // P never touches shared memory: 32 packed fp16 pairs per row -> 32 TMEM columns (word w = keys 2w, 2w+1), read by
+          // the tensor core as the A operand.  Saves the 16 KB of STS, the proxy fence and the MMA's 16 KB re-read per block
+          // (r02q ncu: the TC pipe is busy 48 % of the cycles against 28 % of math -- its shared-memory operand fetches).
+          uint32_t pw[32];
+#pragma unroll
+          for (int unit = 0; unit < 8; ++unit) {
+            pw[unit * 4 + 0] = pk[unit].x;
+            pw[unit * 4 + 1] = pk[unit].y;
+            pw[unit * 4 + 2] = pk[unit].z;
+            pw[unit * 4 + 3] = pk[unit].w;
+          }
+          tmem_st_32x32b_x32(tmem_p + lane_addr, pw);
+          tmem_wait_st();
+        }
         l_run = l_run * alpha + l_blk;
         m_run = m_new;
-        fence_proxy_async_smem();        // P (generic-proxy stores) -> visible to the tensor core's async proxy
+        if (!PTMEM) fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
@@ -416,6 +437,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const 
   if (warp_idx == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PTMEM) tmem_dealloc(tmem_p, C::TMEM_COLS_P);
   }
 }
 

@@ -16,7 +16,6 @@
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_v2.cuh"
 #include "attention_tcgen05_v3.cuh"
-#include "attention_tcgen05_v4.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "gemm_ln_tcgen05.cuh"
@@ -440,20 +439,20 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   // 64 x 512, 69.9 against 80.3 at 128 x 256, bit-identical results).  MEMVUL_ATT_V=1: the first kernel (two CTAs per SM).
   // MEMVUL_ATT_POLY=2: two of every 8 exponentials of the v3 kernel on the FMA pipe (measured slower, 111.5 us: the MUFU
   // pipe is not the limiter even with three streams).
-  static const int att_v = [] { const char* e = getenv("MEMVUL_ATT_V"); int v = e ? atoi(e) : 3; return (v == 1 || v == 2 || v == 4) ? v : 3; }();
-  // MEMVUL_ATT_V=4: two query tiles per CTA in explicit ping-pong (attention_tcgen05_v4.cuh); MEMVUL_ATT4_TOKEN=0 lets its
-  // two contexts run free (diagnostic: what the token itself is worth)
-  static const int att4_token = [] { const char* e = getenv("MEMVUL_ATT4_TOKEN"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  static const int att_v = [] { const char* e = getenv("MEMVUL_ATT_V"); int v = e ? atoi(e) : 3; return (v == 1 || v == 2) ? v : 3; }();
   static const int att_poly = [] { const char* e = getenv("MEMVUL_ATT_POLY"); return (e && atoi(e) == 2) ? 2 : 0; }();
   const bool v1 = att_v == 1;
-  const void* v3_fn = att_poly == 2 ? reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<2>)
-                                    : reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<0>);
+  // MEMVUL_ATT_PTMEM=1: the v3 kernel with P handed to the tensor core through TENSOR memory (tcgen05.st + A-from-TMEM MMA:
+  // no STS, no proxy fence, no 16 KB operand re-read per block).  Parity-green (r02q: 76 GPU tests + C2 / C5 config tests),
+  // but not faster: 108.1 against 107.0 us at 64 x 512 and slower on short sequences (71.8 against 53.4 us at 256 x 128).
+  static const int att_ptmem = [] { const char* e = getenv("MEMVUL_ATT_PTMEM"); return (e && atoi(e) == 1) ? 1 : 0; }();
+  const void* v3_fn = att_ptmem ? reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<0, true>) : att_poly == 2 ? reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<2, false>)
+                                    : reinterpret_cast<const void*>(mv::attention_tcgen05_v3_kernel<0, false>);
   if (v1) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_kernel), mv::AttnCfg::SMEM_BYTES)) return rc; }
   else if (att_v == 2) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v2_kernel), mv::Attn2Cfg::SMEM_BYTES)) return rc; }
-  else if (att_v == 4) { if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(mv::attention_tcgen05_v4_kernel), mv::Attn4Cfg::SMEM_BYTES)) return rc; }
   else { if (int rc = ensure_dyn_smem(v3_fn, mv::Attn3Cfg::SMEM_BYTES)) return rc; }
   const int n_qt = first_tile_only ? 1 : (S + 127) / 128;
-  const int n_items = B * (H / 64) * (att_v == 4 ? (n_qt + 1) / 2 : n_qt);      // v4: an item is a PAIR of query tiles
+  const int n_items = B * (H / 64) * n_qt;
   // MEMVUL_ATT_CTAS_PER_SM=1: diagnostic (one CTA per SM: the soft-max phases without a co-resident CTA's MUFU traffic)
   static const int ctas_env = [] { const char* e = getenv("MEMVUL_ATT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const int ctas_max = att_v == 3 ? mv::Attn3Cfg::CTAS_PER_SM : 2;
@@ -474,14 +473,14 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
     else if (att_v == 2)
       mv::attention_tcgen05_v2_kernel<<<grid, mv::Attn2Cfg::THREADS, mv::Attn2Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), trace_buf);
-    else if (att_v == 4)
-      mv::attention_tcgen05_v4_kernel<<<grid, mv::Attn4Cfg::THREADS, mv::Attn4Cfg::SMEM_BYTES, st>>>(
-          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode(), att4_token);
+    else if (att_ptmem)
+      mv::attention_tcgen05_v3_kernel<0, true><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
+          tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
     else if (att_poly == 2)
-      mv::attention_tcgen05_v3_kernel<2><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
+      mv::attention_tcgen05_v3_kernel<2, false><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
     else
-      mv::attention_tcgen05_v3_kernel<0><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
+      mv::attention_tcgen05_v3_kernel<0, false><<<grid, mv::Attn3Cfg::THREADS, mv::Attn3Cfg::SMEM_BYTES, st>>>(
           tq, tkv, tctx, lens, row_start, reinterpret_cast<__half*>(ctx), B, S, H, n_qt, att_wait_mode());
     CUDA_TRY(cudaGetLastError());
   }

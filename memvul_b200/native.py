@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("MEMVUL_LIB_PATH") or os.path.join(_HERE, "libmemvul_b200.so")   # override: experiment builds (tools/)
 SOURCES = ["memvul_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "gemm_ln_tcgen05.cuh", "attention_tcgen05.cuh",
-           "attention_tcgen05_v2.cuh", "rowwise.cuh", "pool_match.cuh", "precise.cuh"]
+           "attention_tcgen05_v2.cuh", "attention_tcgen05_v3.cuh", "rowwise.cuh", "pool_match.cuh", "precise.cuh"]
 
 ABI_VERSION = 3
 EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32 = 0, 1, 2, 3
