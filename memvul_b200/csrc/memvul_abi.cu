@@ -458,7 +458,8 @@ int attention_impl(const void* qkv, const int32_t* lens, const int32_t* row_star
   const int ctas_max = att_v == 3 ? mv::Attn3Cfg::CTAS_PER_SM : 2;
   const int ctas_per_sm = (ctas_env >= 1 && ctas_env <= ctas_max) ? ctas_env : ctas_max;
   const int grid = n_items < ctas_per_sm * di.sms ? n_items : ctas_per_sm * di.sms;       // persistent: two CTAs per SM
-  // MEMVUL_ATT_TRACE=<file>: debug only -- CTA 0 records clock64() per soft-max / MMA phase (tools/att_trace.py)
+  // MEMVUL_ATT_TRACE=<file>: debug only -- CTA 0 records clock64() per soft-max / MMA phase (tools/att_trace.py; the
+  // MEMVUL_ATT_V=1 / 2 kernels only, like MEMVUL_ATT_{STAGGER,EARLY,SPEC})
   static const char* trace_path = getenv("MEMVUL_ATT_TRACE");
   static unsigned long long* trace_buf = nullptr;
   if (trace_path && !trace_buf) {
