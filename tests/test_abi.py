@@ -30,6 +30,27 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
     assert "HMMA.16" not in sass                                   # no legacy mma.sync path
 
 
+def test_attention_register_pool_balances():
+    """The three-CTA attention kernel re-partitions registers with setmaxnreg (attention_tcgen05_v3.cuh): the soft-max
+    warpgroup rises to 120 and the other drops to 40 from the launch value.  `setmaxnreg.inc` blocks until the CTA's pool
+    holds enough registers, so the kernel only terminates if ptxas really launches it at (120 + 40) / 2 = 80 registers per
+    thread -- and three CTAs only fit if 6 warps x 80 x 32 stays inside a scheduler's 16,384 registers."""
+    from memvul_b200 import native
+    native.build()
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", native.LIB_PATH], capture_output=True, text=True).stdout
+    lines = res.splitlines()
+    regs = [int(re.search(r"REG:(\d+)", lines[i + 1]).group(1)) for i, l in enumerate(lines)
+            if "attention_tcgen05_v3_kernel" in l and i + 1 < len(lines)]
+    assert regs and all(r == 80 for r in regs), regs
+    src = open(os.path.join(os.path.dirname(native.LIB_PATH), "csrc", "attention_tcgen05_v3.cuh")).read()
+    m = re.search(r"REGS_LAUNCH = (\d+), REGS_SOFTMAX = (\d+), REGS_AUX = (\d+)", src)
+    launch, soft, aux = (int(x) for x in m.groups())
+    assert launch == 80 and soft + aux == 2 * launch
+    assert (256 // 32) * 3 // 4 * launch * 32 <= 16384             # 6 warps per scheduler at the launch value
+    sass = subprocess.run(["cuobjdump", "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert f"USETMAXREG.TRY_ALLOC.CTAPOOL UP0, {hex(soft)}" in sass and f"USETMAXREG.DEALLOC.CTAPOOL {hex(aux)}" in sass
+
+
 def test_argument_validation_without_gpu(native_lib):
     L = native_lib
     assert L.memvul_abi_version() == 3
