@@ -213,6 +213,22 @@ def anchor_match_bench(dev, peaks):
     return out
 
 
+def single_thread_figure(O, sd, ids, mask, tids, bank, same_idx, restore_threads: int):
+    """the single-thread figure next to the multi-thread one -- ONE issue report of the sample on one
+    host thread (a few seconds at S = 512)."""
+    import torch
+    S1 = max(1, int(mask[0].sum()))
+    torch.set_num_threads(1)
+    try:
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.memory_forward(sd, ids[:1, :S1].contiguous(), mask[:1, :S1].contiguous(), tids[:1, :S1].contiguous(), bank, same_idx)
+            dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(restore_threads)
+    return {"value": 1.0 / dt, "unit": UNIT, "sample": f"1 issue report, S={S1}, G={bank.shape[0]}, 1 thread, {dt:.1f}s"}
+
+
 def cpu_oracle_throughput(ids, mask, tids, bank, same_idx, budget_s: float = 14.0, batch: int = 8):
     """The reference's CPU path (oracle port) on this box's host cores: a bounded sample of the SAME workload (the
     first rows of the benchmarked batch, in batches of 8).  Returns the timing record and the oracle outputs of the
@@ -237,7 +253,8 @@ def cpu_oracle_throughput(ids, mask, tids, bank, same_idx, budget_s: float = 14.
     rec = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
            "sample": f"{n} issue reports of this run's batch (batches of {batch}, padded to the batch maximum, G={bank.shape[0]}) in {dt:.1f}s, "
                      f"torch {torch.__version__} fp32 CPU, {torch.get_num_threads()} threads",
-           "note": "a stated baseline, not a target: ~0.3 TFLOP/s of fp32 eager PyTorch on host cores"}
+           "note": "a stated baseline, not a target: ~0.3 TFLOP/s of fp32 eager PyTorch on host cores",
+           "single_thread": single_thread_figure(O, sd, ids, mask, tids, bank, same_idx, cores)}
     ref = {k: torch.cat([r[k] for r in refs]) for k in ("logits", "p")}
     return rec, ref, n
 
@@ -270,13 +287,15 @@ def run_reference(args):
                 break
         dt = time.perf_counter() - t0
     v = done * b / dt
+    single = single_thread_figure(O, sd, ids, mask, tids, bank, 0, cores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": min(warm, 2), "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{cfg['name']}; CPU sample of {b} issue reports per step (G={G})",
                        "note": "reference = CPU fp32 PyTorch restatement of ModelMemory.forward (oracle port); AllenNLP is not installable offline"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{done} steps x {b} issue reports, S<={SEQ}, {torch.get_num_threads()} threads"},
+                             "sample": f"{done} steps x {b} issue reports, S<={SEQ}, {torch.get_num_threads()} threads",
+                             "single_thread": single},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
