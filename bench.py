@@ -213,6 +213,20 @@ def anchor_match_bench(dev, peaks):
     return out
 
 
+def host_cpu() -> str:
+    """`lscpu`-style identification of the host the CPU baseline ran on: model name x logical CPUs."""
+    model = "unknown CPU"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return f"{model} x {os.cpu_count()} logical CPUs"
+
+
 def single_thread_figure(O, sd, ids, mask, tids, bank, same_idx, restore_threads: int):
     """the single-thread figure next to the multi-thread one -- ONE issue report of the sample on one
     host thread (a few seconds at S = 512)."""
@@ -254,7 +268,7 @@ def cpu_oracle_throughput(ids, mask, tids, bank, same_idx, budget_s: float = 14.
            "sample": f"{n} issue reports of this run's batch (batches of {batch}, padded to the batch maximum, G={bank.shape[0]}) in {dt:.1f}s, "
                      f"torch {torch.__version__} fp32 CPU, {torch.get_num_threads()} threads",
            "note": "a stated baseline, not a target: ~0.3 TFLOP/s of fp32 eager PyTorch on host cores",
-           "single_thread": single_thread_figure(O, sd, ids, mask, tids, bank, same_idx, cores)}
+           "single_thread": single_thread_figure(O, sd, ids, mask, tids, bank, same_idx, cores), "host": host_cpu()}
     ref = {k: torch.cat([r[k] for r in refs]) for k in ("logits", "p")}
     return rec, ref, n
 
@@ -295,7 +309,7 @@ def run_reference(args):
                        "note": "reference = CPU fp32 PyTorch restatement of ModelMemory.forward (oracle port); AllenNLP is not installable offline"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{done} steps x {b} issue reports, S<={SEQ}, {torch.get_num_threads()} threads",
-                             "single_thread": single},
+                             "single_thread": single, "host": host_cpu()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
