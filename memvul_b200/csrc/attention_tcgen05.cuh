@@ -241,7 +241,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qt = item % n_qt;
       const int h = (item / n_qt) % n_heads;
-      const int b = item / (n_qt * n_heads);
       const int q0 = qt * C::BQ;
       const int len = len_next;
       const size_t row_base = static_cast<size_t>(rb_next);
